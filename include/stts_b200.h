@@ -1,0 +1,134 @@
+/*
+ * stts_b200.h — C ABI of the B200-native VITS acoustic+vocoder engine (libstts_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of huakunyang/SummerTTS: everything that
+ * `SynthesizerTrn::infer` does after the text frontend
+ * (reference: src/models/SynthesizerTrn.cpp:357-396) and the NN half of its constructor
+ * (src/models/SynthesizerTrn.cpp:101-167).  What crosses the boundary is exactly what the
+ * reference passes between its frontend and its NN stack:
+ *      int32 phoneme ids[T], int32 sid, float lengthScale   ->   int16 pcm[S], S
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success and a
+ * negative STTS_E_* code on failure; stts_last_error() gives the message (thread-local).
+ *
+ * Ownership mirrors the reference: the model blob stays owned by the caller and
+ * may be freed after stts_create (weights are repacked into device memory); PCM buffers are
+ * malloc()-compatible and are released with stts_free() (reference: tts_free_data,
+ * src/utils/utils.cpp:34-37).  An engine handle is bound to ONE GPU and ONE caller thread
+ * (the reference's SynthesizerTrn is not re-entrant either: SynthesizerTrn.cpp:338).
+ *
+ * There is no CPU fallback: every entry point that computes fails with STTS_E_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef STTS_B200_H_
+#define STTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STTS_OK 0
+#define STTS_E_ARG (-1)       /* bad argument (null pointer, n < 5 ids, id out of vocabulary ...) */
+#define STTS_E_FORMAT (-2)    /* .bin blob truncated / unknown decoder or duration-predictor type */
+#define STTS_E_UNSUPPORTED (-3) /* hyper-parameters outside what the kernels implement */
+#define STTS_E_CUDA (-4)      /* CUDA runtime failure or no usable device */
+#define STTS_E_NOMEM (-5)
+
+typedef struct stts_engine stts_engine;
+
+/* Replaces: SynthesizerTrn::SynthesizerTrn NN section, src/models/SynthesizerTrn.cpp:91-167.
+ * `model_bytes` is what ttsLoadModel returns (src/utils/utils.cpp:8-32).  Parses the NN section,
+ * repacks the weights into one device arena on GPU `device`.  The frontend tail of the blob is not
+ * touched; its start is reported by stts_nn_end_offset. */
+int stts_create(const float* model_blob, int64_t model_bytes, int device, stts_engine** out);
+
+/* Replaces: SynthesizerTrn::~SynthesizerTrn, src/models/SynthesizerTrn.cpp:403-416. */
+void stts_destroy(stts_engine* e);
+
+/* Float offset at which the frontend tail starts (end of the NN section),
+ * src/models/SynthesizerTrn.cpp:167.  The C++ shim hands the rest to the host text frontend. */
+int64_t stts_nn_end_offset(const stts_engine* e);
+
+/* Raw speaker count of the model (0 for single-speaker files); SynthesizerTrn::getSpeakerNum
+ * (src/models/SynthesizerTrn.cpp:79-89) maps 0 -> 1 in the C++ shim. */
+int32_t stts_speaker_num(const stts_engine* e);
+
+/* Header fields (src/models/SynthesizerTrn.cpp:103-106): 0 isMS, 1 langType, 2 durPredType, 3 decType */
+int32_t stts_header_field(const stts_engine* e, int32_t which);
+
+/* Replaces: the NN half of SynthesizerTrn::infer, src/models/SynthesizerTrn.cpp:357-396.
+ * ids: the phoneme ids produced by the host frontend (:340 / :345-353).  `length_scale` is used as
+ * given (the English 0.83 factor, :354, is applied by the caller/shim).  sid out of range -> 0
+ * (:366-369).  *pcm is malloc'd (free with stts_free), *n_samples = dataLen. */
+int stts_infer_ids(stts_engine* e, const int32_t* ids, int32_t n_ids, int32_t sid, float length_scale,
+                   int16_t** pcm, int32_t* n_samples);
+
+/* Batched form of the same call: B independent utterances, ids concatenated, id_offsets[B+1].
+ * The reference has no batching (it would loop stts_infer_ids); results are identical to the
+ * per-utterance call.  pcm[b] are malloc'd individually; sids / length_scales may be NULL
+ * (0 / 1.0).  Host buffers in, host buffers out: H2D and D2H happen inside the call. */
+int stts_infer_batch(stts_engine* e, int32_t B, const int32_t* ids_concat, const int32_t* id_offsets,
+                     const int32_t* sids, const float* length_scales, int16_t** pcm, int32_t* n_samples);
+
+/* Same, but the PCM of all utterances is written back-to-back into the caller's buffer
+ * `pcm_out` (capacity `cap_samples`, pinned host memory recommended); sample_offsets[B+1]. */
+int stts_infer_batch_into(stts_engine* e, int32_t B, const int32_t* ids_concat, const int32_t* id_offsets,
+                          const int32_t* sids, const float* length_scales, int16_t* pcm_out,
+                          int64_t cap_samples, int64_t* sample_offsets);
+
+/* ---- staged form (bench: inputs resident in HBM before the timed region) ------------------- */
+/* H2D of ids/offsets/sids/length scales into the engine's device staging area. */
+int stts_batch_stage(stts_engine* e, int32_t B, const int32_t* ids_concat, const int32_t* id_offsets,
+                     const int32_t* sids, const float* length_scales);
+/* Runs the whole forward on the staged batch; PCM stays in device memory.  (One 4*(B+1)-byte
+ * device->host read of the frame counts happens inside: the grid of the frame-rate kernels
+ * depends on it, SynthesizerTrn.cpp:376-378.)  Returns total samples in *total_samples. */
+int stts_batch_run(stts_engine* e, int64_t* total_samples);
+/* D2H of the PCM of the last run into pcm_out (capacity cap_samples); sample_offsets[B+1]. */
+int stts_batch_fetch(stts_engine* e, int16_t* pcm_out, int64_t cap_samples, int64_t* sample_offsets);
+
+/* ---- test hooks ---------------------------------------------------------------------------- */
+/* Forced per-id frame counts replacing ceil(exp(logw)*lengthScale) for the NEXT calls (concatenated
+ * over the batch); NULL clears.  Used for shape-stable benches and downstream-stage parity. */
+int stts_set_forced_durations(stts_engine* e, const float* w_ceil, int64_t n);
+
+/* Stage tensors of utterance 0 of the last run, time-major [rows][cols] float32.
+ * which: 0 xx[T][hidden]  1 m[T][inter]  2 logw[T]  3 w_ceil[T]  4 z_p[F][inter]  5 z[F][inter]
+ *        6 o[S] (raw float waveform).  Returns a malloc'd buffer in *out (stts_free). */
+int stts_debug_fetch(stts_engine* e, int32_t which, float** out, int64_t* rows, int64_t* cols);
+
+/* Enable keeping of stage tensors (off by default; costs memory traffic). */
+int stts_debug_enable(stts_engine* e, int32_t on);
+
+/* GPU milliseconds of the last stts_batch_run, from CUDA events on the engine's stream:
+ * ms[0] text encoder, [1] duration predictor (+frame-count sync), [2] length regulator,
+ * [3] flow, [4] decoder, [5] total.  n = capacity of ms. */
+int stts_last_timing(const stts_engine* e, float* ms, int32_t n);
+
+/* Number of kernels this library launched since creation (all are ours: no cuBLAS/cuDNN). */
+int64_t stts_kernel_launches(const stts_engine* e);
+
+/* The cudaStream_t (as void*) all kernels of this engine are launched on. */
+void* stts_stream(const stts_engine* e);
+
+/* Conv path selection: 0 = fp32 CUDA-core tiles everywhere, 1 = tcgen05 tensor-core tiles
+ * (split-bf16, fp32-accurate) where a layer is eligible.  Default 1 when the build has it. */
+int stts_set_tensor_path(stts_engine* e, int32_t mode);
+
+/* Replaces: tts_free_data, src/utils/utils.cpp:34-37. */
+void stts_free(void* p);
+
+const char* stts_last_error(void);
+
+/* Host-only: parse the NN section and return a malloc'd text description of the layer graph
+ * (one line per record) — no GPU needed.  Used by the CPU test-suite to check the parser against
+ * summertts_b200/binfmt.py.  *nn_end receives the float offset of the frontend tail. */
+int stts_describe_model(const float* model_blob, int64_t model_bytes, char** text, int64_t* nn_end);
+
+const char* stts_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STTS_B200_H_ */
