@@ -106,6 +106,24 @@ int stts_debug_enable(stts_engine* e, int32_t on);
  * [3] flow, [4] decoder, [5] total.  n = capacity of ms. */
 int stts_last_timing(const stts_engine* e, float* ms, int32_t n);
 
+/* Per-kernel-class profiler: when enabled, every dense-conv launch of stts_batch_run is bracketed
+ * by CUDA events on the engine's stream; fetch returns, per class, the summed GPU milliseconds, the
+ * ALGORITHMIC flops (2*MACs of the un-expanded, un-padded convolution) and the launch count
+ * accumulated since the last enable.  Arrays have STTS_NUM_CLS entries. */
+#define STTS_NUM_CLS 10
+#define STTS_CLS_OTHER 0
+#define STTS_CLS_ENC 1       /* text-encoder 1x1 / FFN convs (attention excluded) */
+#define STTS_CLS_DP 2        /* duration-predictor convs */
+#define STTS_CLS_FLOW_IO 3   /* coupling pre / post 1x1 */
+#define STTS_CLS_WN_IN 4     /* WN in_layers k5 C->2C with the gate epilogue */
+#define STTS_CLS_WN_RS 5     /* WN res_skip 1x1 */
+#define STTS_CLS_DEC_PRE 6   /* conv_pre */
+#define STTS_CLS_DEC_UP 7    /* ConvTranspose1d upsamplers */
+#define STTS_CLS_DEC_RB 8    /* MRF ResBlock1 convs */
+#define STTS_CLS_DEC_TAIL 9  /* conv_post / subband_conv_post */
+int stts_profile_enable(stts_engine* e, int32_t on);
+int stts_profile_fetch(const stts_engine* e, double* ms, double* flops, int64_t* launches);
+
 /* Number of kernels this library launched since creation (all are ours: no cuBLAS/cuDNN). */
 int64_t stts_kernel_launches(const stts_engine* e);
 

@@ -53,6 +53,7 @@ struct DConv {
     float* w = nullptr;  // [k][Cin][CoutW]
     float* b = nullptr;  // [Cout] or null
     int Cin = 0, Cout = 0, CoutW = 0, k = 1, dil = 1, padl = 0;
+    double macs_row = 0;  // algorithmic MACs per input-rate row (un-expanded taps, live outputs only)
 #ifdef STTS_WITH_TC
     TcWeights tc;        // split-bf16 UMMA-layout copy (filled when the layer is tensor-path eligible)
 #endif
@@ -186,6 +187,33 @@ struct stts_engine {
     } dbg;
     cudaEvent_t ev[7] = {};
     float lastMs[6] = {};
+    // per-kernel-class profiler (CUDA events around each conv launch; off by default)
+    struct ProfRec { int cls; cudaEvent_t a, b; double flops; };
+    bool profOn = false;
+    std::vector<cudaEvent_t> profPool;
+    size_t profUsed = 0;
+    std::vector<ProfRec> profRecs;
+    double profMs[STTS_NUM_CLS] = {}, profFlops[STTS_NUM_CLS] = {};
+    int64_t profLaunch[STTS_NUM_CLS] = {};
+    int64_t curRowsTotal = 0;  // total live rows of the convs being launched (set by run())
+    int curCls = 0;
+    cudaEvent_t prof_event() {
+        if (profUsed == profPool.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            profPool.push_back(e);
+        }
+        return profPool[profUsed++];
+    }
+    void prof_collect() {
+        for (auto& r : profRecs) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+            profMs[r.cls] += ms; profFlops[r.cls] += r.flops; profLaunch[r.cls] += 1;
+        }
+        profRecs.clear();
+        profUsed = 0;
+    }
 
     // ---- helpers ---------------------------------------------------------------------------
     template <typename T>
@@ -229,6 +257,7 @@ struct stts_engine {
                 }
         }
         d.w = upload(w);
+        d.macs_row = (double)d.Cout * d.Cin * d.k;
         if (r.hasBias == 1) {
             std::vector<float> b(d.Cout);
             for (int o = 0; o < d.Cout; ++o) b[o] = sign * r.b[omap.empty() ? o : omap[o]];
@@ -268,6 +297,7 @@ struct stts_engine {
                         w[((size_t)j * d.Cin + c) * d.CoutW + ph * r.outCh + o] = r.w[((size_t)o * k + kk) * r.inCh + c];
             }
         d.w = upload(w);
+        d.macs_row = (double)r.outCh * r.inCh * r.k;  // per INPUT row: every x row meets every tap once
         if (r.hasBias == 1) {
             std::vector<float> b(d.Cout);
             for (int ph = 0; ph < s; ++ph)
@@ -317,6 +347,17 @@ struct stts_engine {
     void conv(const DConv& c, const float* x, int ldx, float* y, int ldy, Seg seg, int nseg, int maxlen,
               const ConvOpts& o = ConvOpts()) {
         if (maxlen <= 0 || nseg <= 0) return;
+        if (!profOn) { conv_impl(c, x, ldx, y, ldy, seg, nseg, maxlen, o); return; }
+        ProfRec r;
+        r.cls = curCls; r.a = prof_event(); r.b = prof_event();
+        r.flops = 2.0 * c.macs_row * (double)curRowsTotal;
+        CUDA_CHECK(cudaEventRecord(r.a, stream));
+        conv_impl(c, x, ldx, y, ldy, seg, nseg, maxlen, o);
+        CUDA_CHECK(cudaEventRecord(r.b, stream));
+        profRecs.push_back(r);
+    }
+    void conv_impl(const DConv& c, const float* x, int ldx, float* y, int ldy, Seg seg, int nseg, int maxlen,
+                   const ConvOpts& o) {
         ConvP p;
         p.x = x; p.ldx = ldx; p.w = c.w; p.CoutW = c.CoutW; p.bias = c.b; p.y = y; p.ldy = ldy;
         p.y2 = o.y2; p.ldy2 = o.ldy2; p.res = o.res; p.ldr = o.ldr; p.gvec = o.gvec; p.ldg = o.ldg;
@@ -416,6 +457,7 @@ void stts_engine::build(const Model& M) {
                     b[s * hidden + o] = src[s]->hasBias == 1 ? src[s]->b[o] : 0.f;
                 }
             d.w = upload(w); d.b = upload(b);
+            d.macs_row = (double)d.Cout * d.Cin;
 #ifdef STTS_WITH_TC
             tc_prepare_weights(d.tc, w.data(), 1, d.Cin, d.Cout, d.CoutW, owned);
 #endif
@@ -675,6 +717,7 @@ void stts_engine::run() {
     const size_t tokEnd = ws.off;
 
     // ---- speaker conditioning vectors (SynthesizerTrn.cpp:363-372; cond convs of DP / WN / decoder)
+    curCls = STTS_CLS_OTHER; curRowsTotal = B;
     if (isMS) {
         spk_gather_kernel<<<(B * gin + 255) / 256, 256, 0, stream>>>(emg, d_sids, G, B, gin, spkNum);
         launch_check();
@@ -687,6 +730,7 @@ void stts_engine::run() {
     }
 
     // ---- text encoder (TextEncoder.cpp:50-74, attention_encoder.cpp:78-94) ---------------------
+    curCls = STTS_CLS_ENC; curRowsTotal = Tt;
     embed_kernel<<<((size_t)Tt * H + 255) / 256, 256, 0, stream>>>(d_ids, emb, x, Tt, H, vocab, std::sqrt((float)H));
     launch_check();
     for (int i = 0; i < nEnc; ++i) {
@@ -712,6 +756,7 @@ void stts_engine::run() {
     CUDA_CHECK(cudaEventRecord(ev[1], stream));
 
     // ---- duration predictor ------------------------------------------------------------------
+    curCls = STTS_CLS_DP;
     if (durPredType == 1) {
         // FixDurationPredictor::forward, src/models/FixDurationPredictor.cpp:75-96
         const float* xin = x;
@@ -835,17 +880,21 @@ void stts_engine::run() {
         const int parity = (flowN - i) % 2;
         const float* x0 = z + (parity ? half : 0);
         float* x1p = z + (parity ? 0 : half);
+        curRowsTotal = Ft; curCls = STTS_CLS_FLOW_IO;
         conv(L.pre, x0, inter, hbuf, WH, fseg, B, maxF);                        // h = pre(x0)
         const int nl = (int)L.in.size();
         for (int l = 0; l < nl; ++l) {                                          // WN::forward, WN.cpp:100-149
             ConvOpts g; g.epi = EPI_GATE;
             if (L.hasCond) { g.gvec = gWn[i] + (size_t)l * 2 * WH; g.ldg = L.cond.Cout; }
+            curCls = STTS_CLS_WN_IN;
             conv(L.in[l], hbuf, WH, acts, WH, fseg, B, maxF, g);
             ConvOpts r; r.epi = EPI_RESSKIP; r.y2 = skip; r.ldy2 = WH; r.y2_store = (l == 0);
             r.split = (l < nl - 1) ? WH : 0;
+            curCls = STTS_CLS_WN_RS;
             conv(L.rs[l], acts, WH, hbuf, WH, fseg, B, maxF, r);
         }
         ConvOpts a; a.epi = EPI_ACCUM;
+        curCls = STTS_CLS_FLOW_IO;
         conv(L.post, skip, WH, x1p, inter, fseg, B, maxF, a);                   // x1 = x1 - post(h)
     }
     if (flowN % 2 == 1) {
@@ -859,6 +908,7 @@ void stts_engine::run() {
     {
         ConvOpts o;
         if (gDec) { o.gvec = gDec; o.ldg = decCond.Cout; }
+        curCls = STTS_CLS_DEC_PRE; curRowsTotal = Ft;
         conv(convPre, z, inter, cur, convPre.Cout, fseg, B, maxF, o);            // conv_pre (+ cond(g))
     }
     int rate = 1, curC = convPre.Cout;
@@ -873,9 +923,11 @@ void stts_engine::run() {
         float* accb = ws.get<float>(rows * C);
         {   // leaky(0.1) + ConvTranspose1d (phase-expanded): Generator_MS.cpp:172-175
             ConvOpts o; o.in_act = ACT_LEAKY; o.in_slope = 0.1f;
+            curCls = STTS_CLS_DEC_UP; curRowsTotal = (int64_t)Ft * rate_in;
             conv(ups[s], cur, curC, xx, upRates[s] * C, Seg{d_foff, rate_in, 0}, B, maxF * rate_in, o);
         }
         const Seg sseg{d_foff, rate, 0};
+        curCls = STTS_CLS_DEC_RB; curRowsTotal = (int64_t)Ft * rate;
         const int ml = maxF * rate;
         for (int j = 0; j < nRbK; ++j) {                                         // MRF: Generator_MS.cpp:177-196
             RB& rb = rbs[s * nRbK + j];
@@ -899,6 +951,7 @@ void stts_engine::run() {
         cur = accb; curC = C;
     }
     float* o = ws.get<float>((size_t)std::max<int64_t>(St, 1));
+    curCls = STTS_CLS_DEC_TAIL; curRowsTotal = (int64_t)Ft * rate;
     if (decType == 0) {
         // leaky(0.01) -> conv_post -> tanh: Generator_hifigan.cpp:176-180
         ConvOpts t; t.in_act = ACT_LEAKY; t.in_slope = 0.01f; t.epi = EPI_TANH; t.allow_tc = false;
@@ -939,6 +992,7 @@ void stts_engine::run() {
     CUDA_CHECK(cudaStreamSynchronize(stream));
     for (int i = 0; i < 5; ++i) CUDA_CHECK(cudaEventElapsedTime(&lastMs[i], ev[i], ev[i + 1]));
     CUDA_CHECK(cudaEventElapsedTime(&lastMs[5], ev[0], ev[5]));
+    if (profOn) prof_collect();
     const int sMul = R * tailMul;
     h_soff.assign(B + 1, 0);
     for (int u = 0; u <= B; ++u) h_soff[u] = (int64_t)h_foff[u] * sMul;
@@ -1023,6 +1077,7 @@ void stts_destroy(stts_engine* e) {
     if (e->hostPcm) cudaFreeHost(e->hostPcm);
     if (e->hostInts) cudaFreeHost(e->hostInts);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->profPool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1147,6 +1202,18 @@ int stts_debug_fetch(stts_engine* e, int32_t which, float** out, int64_t* rows, 
         CUDA_CHECK(cudaMemcpy(*out, src, (size_t)(r * c) * 4, cudaMemcpyDeviceToHost));
         *rows = r; *cols = c;
     });
+}
+
+int stts_profile_enable(stts_engine* e, int32_t on) {
+    if (!e) return STTS_E_ARG;
+    e->profOn = on != 0;
+    for (int i = 0; i < STTS_NUM_CLS; ++i) { e->profMs[i] = 0; e->profFlops[i] = 0; e->profLaunch[i] = 0; }
+    return STTS_OK;
+}
+int stts_profile_fetch(const stts_engine* e, double* ms, double* flops, int64_t* launches) {
+    if (!e || !ms || !flops || !launches) return STTS_E_ARG;
+    for (int i = 0; i < STTS_NUM_CLS; ++i) { ms[i] = e->profMs[i]; flops[i] = e->profFlops[i]; launches[i] = e->profLaunch[i]; }
+    return STTS_OK;
 }
 
 int stts_last_timing(const stts_engine* e, float* ms, int32_t n) {

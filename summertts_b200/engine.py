@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "stts_infer_ids", "stts_infer_batch", "stts_infer_batch_into", "stts_batch_stage", "stts_batch_run",
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
-    "stts_describe_model", "stts_version",
+    "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
 ]
 
 _lib = None
@@ -66,6 +66,8 @@ def load_library():
     L.stts_debug_fetch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.stts_debug_enable.argtypes = [vp, i32]
     L.stts_last_timing.argtypes = [vp, vp, i32]
+    L.stts_profile_enable.argtypes = [vp, i32]
+    L.stts_profile_fetch.argtypes = [vp, vp, vp, vp]
     L.stts_kernel_launches.argtypes = [vp]
     L.stts_kernel_launches.restype = i64
     L.stts_stream.argtypes = [vp]
@@ -202,6 +204,17 @@ class SynthesizerTrn:
         ms = (C.c_float * 6)()
         _check(self._L.stts_last_timing(self._h, ms, 6))
         return dict(zip(("enc", "dp", "regulate", "flow", "dec", "total"), [float(v) for v in ms]))
+
+    CLASSES = ("other", "enc", "dp", "flow_io", "wn_in", "wn_rs", "dec_pre", "dec_up", "dec_rb", "dec_tail")
+
+    def profile_enable(self, on=True):
+        _check(self._L.stts_profile_enable(self._h, 1 if on else 0))
+
+    def profile_fetch(self) -> dict:
+        n = len(self.CLASSES)
+        ms, fl, ln = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        _check(self._L.stts_profile_fetch(self._h, ms, fl, ln))
+        return {c: dict(ms=ms[i], flops=fl[i], launches=int(ln[i])) for i, c in enumerate(self.CLASSES)}
 
     def kernel_launches(self) -> int:
         return int(self._L.stts_kernel_launches(self._h))

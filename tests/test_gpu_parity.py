@@ -1,0 +1,192 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(include/stts_b200.h via summertts_b200.engine) and is compared with
+  * the committed golden vectors produced by the compiled, unmodified reference, and
+  * the compiled reference itself (oracle/_ref) when it travelled to the box.
+Tolerances (fp32 path): frame counts / w_ceil exact; float waveform max|a-b|/max|b| <= 1e-3
+(BASELINE.json); int16 PCM <= 1 LSB except on at most 1e-4 of the samples and never more than
+2 LSB for `fast`/`multi`/synthetic models (the reference itself moves 1 LSB on ~1% of samples when only
+its OpenMP thread count changes); `mid` <= 12 LSB (its own fp32 noise floor is 7-9 LSB).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+from parity_util import GOLDEN, TEST_TXT_IDS, find_model, lsb_diff, rel_err, synth_ids
+
+from oracle import ref
+from summertts_b200 import binfmt, engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _pcm_ok(a, b, max_lsb=2, frac=1e-4):
+    assert a.size == b.size
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    assert d.max() <= max_lsb, "max LSB diff %d" % d.max()
+    assert (d > 1).sum() <= max(1, int(frac * a.size)), "%d samples differ by more than 1 LSB" % (d > 1).sum()
+
+
+@pytest.fixture(scope="module")
+def fast_blob():
+    b = find_model("single_speaker_fast")
+    if b is None:
+        b = binfmt.synthetic_model(seed=11)  # same architecture, random weights
+    return b
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "synth_*.npz"))))
+def test_synthetic_models_vs_golden(native_lib, path):
+    """All four decoder variants, both duration predictors, speaker conditioning — including
+    Generator_Istft / Generator_MBB+PQMF which no shipped model reaches."""
+    g = np.load(path)
+    blob = binfmt.synthetic_model(seed=int(g["seed"]), **json.loads(str(g["hp"])))
+    E = engine.SynthesizerTrn(blob)
+    E.debug_enable(True)
+    for pre, forced in (("a", None), ("b", g["forced"])):
+        E.set_forced_durations(forced)
+        pcm = E.infer_ids(g["ids"], int(g["sid"]), 1.0)
+        assert np.array_equal(E.debug_fetch("w_ceil"), g[pre + "_wceil"])
+        assert pcm.size == g[pre + "_pcm"].size
+        assert rel_err(E.debug_fetch("z"), g[pre + "_z"]) < 1e-4
+        assert rel_err(E.debug_fetch("o"), g[pre + "_o"]) < 1e-4
+        _pcm_ok(pcm, g[pre + "_pcm"])
+        if pre == "a":
+            assert rel_err(E.debug_fetch("xx"), g["a_xx"]) < 1e-4
+            assert rel_err(E.debug_fetch("m"), g["a_m"]) < 1e-4
+            assert rel_err(E.debug_fetch("logw"), g["a_logw"]) < 1e-4
+    E.close()
+
+
+@pytest.mark.parametrize("name,max_lsb,frac", [("single_speaker_fast", 2, 1e-4), ("multi_speakers", 2, 1e-4),
+                                               ("single_speaker_mid", 12, 2e-2), ("single_speaker_english_fast", 4, 1e-3)])
+def test_shipped_models_vs_golden(native_lib, name, max_lsb, frac):
+    """BASELINE configs 2-4: shipped weights, reference ids, fp32 parity within 1e-3."""
+    blob = find_model(name)
+    if blob is None:
+        pytest.skip("shipped weights did not travel to this box")
+    g = np.load(os.path.join(GOLDEN, "real_%s.npz" % name))
+    E = engine.SynthesizerTrn(blob)
+    E.debug_enable(True)
+    pcm = E.infer_ids(g["ids"], int(g["sid"]), float(g["ls"]))
+    assert np.array_equal(E.debug_fetch("w_ceil"), g["wceil"])
+    assert pcm.size == g["pcm"].size
+    assert rel_err(E.debug_fetch("o"), g["o"]) < 1e-3
+    _pcm_ok(pcm, g["pcm"], max_lsb, frac)
+    E.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel")
+def test_long_form_vs_compiled_reference(native_lib, fast_blob):
+    """Config 3 style long-form: the id sequence repeated x4 as ONE utterance through the oracle."""
+    ref.set_threads(8)
+    ids = (TEST_TXT_IDS[:-1] * 4) + [1]
+    r = ref.RefModel(fast_blob).infer(ids, dumps=True)
+    E = engine.SynthesizerTrn(fast_blob)
+    E.debug_enable(True)
+    pcm = E.infer_ids(ids)
+    assert np.array_equal(E.debug_fetch("w_ceil"), r.w_ceil)
+    assert rel_err(E.debug_fetch("o"), r.o) < 1e-3
+    _pcm_ok(pcm, r.pcm, 3, 1e-3)
+    E.close()
+
+
+def test_batch_equals_per_utterance_ragged(native_lib, fast_blob):
+    """Packed varlen batch == the same utterances one at a time (bit-exact): every conv pads at its own
+    utterance's edges, exactly as the batch-1 reference does."""
+    rng = np.random.default_rng(5)
+    E = engine.SynthesizerTrn(fast_blob)
+    lens = [5, 128, 17, 64, 9, 33]
+    utts = [synth_ids(rng, n) for n in lens]
+    single = [E.infer_ids(u) for u in utts]
+    batch = E.infer_batch(utts)
+    for a, b in zip(single, batch):
+        assert np.array_equal(a, b)
+    # permutation invariance
+    perm = [3, 0, 5, 1, 4, 2]
+    batch2 = E.infer_batch([utts[i] for i in perm])
+    for k, i in enumerate(perm):
+        assert np.array_equal(batch2[k], single[i])
+    # determinism
+    assert all(np.array_equal(a, b) for a, b in zip(batch, E.infer_batch(utts)))
+    E.close()
+
+
+def test_full_size_batch_properties(native_lib, fast_blob):
+    """BASELINE config-5 shape (64 x 128 ids, forced 5 frames/id): size-independent checks —
+    S = 256 * sum(w_ceil) per utterance, identical utterances give identical PCM, and a sampled
+    utterance equals its stand-alone run."""
+    rng = np.random.default_rng(1234)
+    E = engine.SynthesizerTrn(fast_blob)
+    base = [synth_ids(rng, 128) for _ in range(8)]
+    utts = [base[i % 8] for i in range(64)]
+    E.set_forced_durations(np.full(64 * 128, 5.0, np.float32))
+    out = E.infer_batch(utts)
+    assert all(o.size == 128 * 5 * 256 for o in out)
+    for i in range(8, 64):
+        assert np.array_equal(out[i], out[i % 8])
+    E.set_forced_durations(np.full(128, 5.0, np.float32))
+    assert np.array_equal(E.infer_ids(base[3]), out[3])
+    E.close()
+
+
+def test_edge_cases(native_lib, fast_blob):
+    E = engine.SynthesizerTrn(fast_blob)
+    rng = np.random.default_rng(9)
+    # fewer than win+1 = 5 ids: the reference cannot run (multi_head_attention.cpp:140-150) -> STTS_E_ARG
+    with pytest.raises(engine.SttsError) as ei:
+        E.infer_ids([0, 15, 119, 1])
+    assert ei.value.code == -1
+    with pytest.raises(engine.SttsError):
+        E.infer_ids([0, 15, 5000, 3, 1, 1])  # id outside the vocabulary
+    # minimum length works
+    assert E.infer_ids(synth_ids(rng, 5)).size % 256 == 0
+    # zero-duration tokens (forced) and the all-zero case: frames = max(sum, 1) (nn_clamp_min, SynthesizerTrn.cpp:378)
+    ids = synth_ids(rng, 12)
+    w = np.array([0, 3, 0, 0, 2, 1, 0, 4, 0, 0, 1, 0], np.float32)
+    E.set_forced_durations(w)
+    assert E.infer_ids(ids).size == int(w.sum()) * 256
+    E.set_forced_durations(np.zeros(12, np.float32))
+    assert E.infer_ids(ids).size == 256
+    E.set_forced_durations(None)
+    E.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref did not travel")
+def test_zero_duration_matches_reference(native_lib):
+    blob = binfmt.synthetic_model(seed=100, decType=1, durPredType=1, isMS=0, nLayers=2, preCh=32)
+    rng = np.random.default_rng(3)
+    ids = synth_ids(rng, 12)
+    w = np.array([0, 3, 0, 0, 2, 1, 0, 4, 0, 0, 1, 0], np.float32)
+    ref.set_threads(1)
+    r = ref.RefModel(blob).infer(ids, forced_w=w)
+    E = engine.SynthesizerTrn(blob)
+    E.set_forced_durations(w)
+    _pcm_ok(E.infer_ids(ids), r.pcm)
+    E.close()
+
+
+def test_speaker_id_clamp(native_lib):
+    """sid out of range behaves as sid 0 (SynthesizerTrn.cpp:366-369)."""
+    blob = binfmt.synthetic_model(seed=104, decType=0, durPredType=1, isMS=1, nLayers=2, preCh=32, spkNum=5, gin=32,
+                                  upRates=(4, 2, 2), upK=(8, 4, 4))
+    rng = np.random.default_rng(4)
+    ids = synth_ids(rng, 20)
+    E = engine.SynthesizerTrn(blob)
+    assert E.getSpeakerNum() == 5
+    a0 = E.infer_ids(ids, sid=0)
+    assert np.array_equal(E.infer_ids(ids, sid=99), a0)
+    assert np.array_equal(E.infer_ids(ids, sid=-1), a0)
+    assert not np.array_equal(E.infer_ids(ids, sid=2), a0)
+    E.close()
+
+
+def test_native_kernels_ran(native_lib, fast_blob):
+    E = engine.SynthesizerTrn(fast_blob)
+    n0 = E.kernel_launches()
+    E.infer_ids(TEST_TXT_IDS)
+    assert E.kernel_launches() - n0 > 50
+    t = E.last_timing()
+    assert t["total"] > 0 and t["flow"] > 0 and t["dec"] > 0
+    E.close()
