@@ -134,6 +134,15 @@ void* stts_stream(const stts_engine* e);
  * (split-bf16, fp32-accurate) where a layer is eligible.  Default 1 when the build has it. */
 int stts_set_tensor_path(stts_engine* e, int32_t mode);
 
+/* Op-level test hook (tests only): runs ONE conv1d record (file format of nn_conv1d.cpp:25-52, or the
+ * ConvTranspose1d record of nn_conv1d_transposed.cpp:25-52 when transposed != 0) on x[T][inCh] through
+ * the fp32 FFMA tiles (use_tc = 0) or the tcgen05 path (use_tc = 1).  seg_off[nseg+1] packs several
+ * utterances (NULL = one).  in_act: 0 none / 1 leaky(slope); epi: 0 store, 1 relu, 4 WN gate, 6 tanh.
+ * Returns y (malloc'd, [rows][cols]). */
+int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_floats, int transposed, int stride,
+                     int pad_override, int dil_override, const float* x, int T, int nseg, const int* seg_off,
+                     int in_act, float slope, int epi, float** y, int* rows, int* cols);
+
 /* Replaces: tts_free_data, src/utils/utils.cpp:34-37. */
 void stts_free(void* p);
 

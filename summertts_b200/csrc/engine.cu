@@ -1216,6 +1216,59 @@ int stts_profile_fetch(const stts_engine* e, double* ms, double* flops, int64_t*
     return STTS_OK;
 }
 
+// Op-level test hook: one conv (or ConvTranspose1d) through the FFMA tiles (use_tc == 0) or the
+// tcgen05 path (use_tc == 1) on caller-provided data.  x: [T][Cin] with optional utterance offsets.
+int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_floats, int transposed, int stride,
+                     int pad_override, int dil_override, const float* x, int T, int nseg, const int* seg_off,
+                     int in_act, float slope, int epi, float** y, int* rows, int* cols) {
+    stts_engine* e = nullptr;
+    int rc = guard([&] {
+        if (!rec || !x || !y || !rows || !cols) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(device));
+        e = new stts_engine();
+        e->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        Cursor c{rec, rec_floats};
+        ConvRec r = transposed ? parse_convT(c) : parse_conv(c);
+        if (pad_override >= 0) r.pad = pad_override;
+        if (dil_override > 0) r.dil = dil_override;
+        if (transposed) r.stride = stride;
+        DConv d;
+        if (transposed) d = e->make_convT(r);
+        else if (epi == EPI_GATE) {
+            const int H = r.outCh / 2;
+            std::vector<int> gm(2 * H);
+            for (int j = 0; j < H; ++j) { gm[2 * j] = j; gm[2 * j + 1] = H + j; }
+            d = e->make_conv(r, gm);
+        } else d = e->make_conv(r);
+        e->tensor_mode = use_tc;
+#ifdef STTS_WITH_TC
+        if (use_tc && !d.tc.ok) throw Unsupported("layer is not eligible for the tensor-core path");
+#else
+        if (use_tc) throw Unsupported("this build has no tensor-core path");
+#endif
+        std::vector<int> so;
+        if (seg_off) so.assign(seg_off, seg_off + nseg + 1); else { nseg = 1; so = {0, T}; }
+        int maxlen = 0;
+        for (int i = 0; i < nseg; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+        int* dso = e->dalloc<int>(so.size());
+        CUDA_CHECK(cudaMemcpy(dso, so.data(), so.size() * 4, cudaMemcpyHostToDevice));
+        float* dx = e->upload(x, (size_t)T * r.inCh);
+        const int outC = epi == EPI_GATE ? d.Cout / 2 : (transposed ? r.outCh : d.Cout);
+        const int outRows = transposed ? T * r.stride : T;
+        float* dy = e->dalloc<float>((size_t)outRows * outC);
+        CUDA_CHECK(cudaMemset(dy, 0, (size_t)outRows * outC * 4));
+        ConvOpts o; o.in_act = in_act; o.in_slope = slope; o.epi = epi;
+        e->conv(d, dx, r.inCh, dy, transposed ? d.Cout : outC, Seg{dso, 1, 0}, nseg, maxlen, o);
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        *y = (float*)malloc((size_t)outRows * outC * 4);
+        CUDA_CHECK(cudaMemcpy(*y, dy, (size_t)outRows * outC * 4, cudaMemcpyDeviceToHost));
+        *rows = outRows; *cols = outC;
+    });
+    if (e) stts_destroy(e);
+    return rc;
+}
+
 int stts_last_timing(const stts_engine* e, float* ms, int32_t n) {
     if (!e || !ms) return STTS_E_ARG;
     for (int i = 0; i < n && i < 6; ++i) ms[i] = e->lastMs[i];

@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
+    "stts_test_conv1d",
 ]
 
 _lib = None
@@ -68,6 +69,8 @@ def load_library():
     L.stts_last_timing.argtypes = [vp, vp, i32]
     L.stts_profile_enable.argtypes = [vp, i32]
     L.stts_profile_fetch.argtypes = [vp, vp, vp, vp]
+    L.stts_test_conv1d.argtypes = [C.c_int, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp,
+                                   C.c_int, f32, C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.stts_kernel_launches.argtypes = [vp]
     L.stts_kernel_launches.restype = i64
     L.stts_stream.argtypes = [vp]
@@ -235,6 +238,24 @@ class SynthesizerTrn:
             self.close()
         except Exception:
             pass
+
+
+def test_conv1d(rec, x, use_tc=0, transposed=False, stride=1, pad=-1, dil=0, seg_off=None, in_act=0, slope=0.0, epi=0,
+                device=0):
+    """Op-level hook: one conv record through the FFMA tiles or the tcgen05 path (tests only)."""
+    L = load_library()
+    rec = np.ascontiguousarray(rec, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    so = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int32)
+    y, r, c = C.c_void_p(), C.c_int(), C.c_int()
+    _check(L.stts_test_conv1d(device, int(use_tc), rec.ctypes.data, rec.size, 1 if transposed else 0, int(stride), int(pad),
+                              int(dil), x.ctypes.data, x.shape[0], 0 if so is None else so.size - 1,
+                              None if so is None else so.ctypes.data, int(in_act), float(slope), int(epi),
+                              C.byref(y), C.byref(r), C.byref(c)))
+    n = r.value * c.value
+    out = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_float)), shape=(n,)).copy().reshape(r.value, c.value)
+    L.stts_free(y)
+    return out
 
 
 def ttsLoadModel(path: str) -> np.ndarray:
