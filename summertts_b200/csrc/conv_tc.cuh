@@ -6,8 +6,12 @@
 //
 // GEMM orientation (per CTA): D[128 time rows x NC out-channels] (fp32, in TMEM)
 //        += sum over taps, sum over 16-channel K-steps  A_tap[128 x 16] * W_tap[NC x 16]^T
-//  * A operand: the activation tile is staged ONCE per 32-channel chunk as fp16 in shared memory in
-//    the no-swizzle K-major core-matrix layout  addr(row, c) = (c/8)*(ROWS*16B) + row*16B + (c%8)*2B.
+//  * A operand: activations live in HBM as split-fp16 "planes" in the chunk-major layout
+//    plane[c/8][padded row][c%8] (hi plane, then lo plane), written once by the PRODUCER of the tensor
+//    (conv epilogue) or by split_planes_kernel.  One TMA box (8, rows, KC/8) per plane and K-chunk
+//    (cp.async.bulk.tensor.3d -> mbarrier complete_tx) lands in shared memory directly in
+//    the no-swizzle K-major core-matrix layout  addr(row, c) = (c/8)*(ROWS*16B) + row*16B + (c%8)*2B;
+//    GAP zero rows between utterances + TMA out-of-bounds zero fill give every conv its zero padding.
 //    A tap at dilation d is the SAME tile with the descriptor start address advanced by tap*d rows
 //    (16 B per row) — no im2col, no per-tap reload, no zero-stuffed dilated kernel (the reference
 //    materialises both: nn_conv1d.cpp:133-155,184-187).
@@ -25,24 +29,30 @@
 //    warps drain the `main` TMEM accumulator (tcgen05.ld, round-to-nearest adds) while they refill the
 //    A tile, and the next chunk restarts it with accumulate = 0.  The lo*hi / hi*lo correction terms
 //    (2^-11 of the magnitude) accumulate in a second TMEM accumulator for the whole tile.
-//  * warp roles: warps 0-3 stage A tiles (fp32 -> leaky-relu -> split fp16 -> st.shared) and later run
-//    the epilogue (tcgen05.ld -> bias / gate / residual / ... -> global); warp 4 lane 0 issues the MMAs;
-//    warp 5 lane 0 streams weights.  mbarriers connect them; tcgen05.commit releases smem stages.
+//  * warp roles: warps 0-3 promote partial sums and run the epilogue (tcgen05.ld -> bias / gate /
+//    residual / ... -> fp32 rows and/or split-fp16 planes for the next conv); warp 4 lane 0 issues the
+//    MMAs; warp 5 lane 0 streams weights; warp 6 lane 0 streams activation tiles (TMA).  mbarriers
+//    connect them; tcgen05.commit releases smem stages.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.cuh"
 
 namespace stts {
 
-constexpr int TC_STAGES = 3;       // weight ring depth
-constexpr int TC_THREADS = 192;    // 4 loader/epilogue warps + MMA warp + weight-producer warp
+constexpr int TC_MAX_RING = 16;    // max weight ring depth (chosen per launch to fill shared memory)
+constexpr int TC_MAX_ARING = 4;    // max activation ring depth
+constexpr int TC_THREADS = 352;    // 2 x 4 promotion/epilogue warps (even / odd tiles) + MMA warp + weight-producer warp + activation-TMA warp
+constexpr int TC_GAP = 64;         // zero rows kept before/after every utterance in the fp16 planes (>= max conv halo)
 constexpr float TC_ASCALE = 8.0f;  // 2^3 activation pre-scale
 
 struct TcWeights {
@@ -123,6 +133,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// Warp-collective wait: ONE lane polls (with back-off) and the warp re-converges.  All-lane polling
+// floods the shared-memory pipe the tensor core fetches its operands through (measured: MMA issue
+// slowed 3x with 256 spinning threads).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* b, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(b, parity);
+    __syncwarp();
+}
+// elect.sync: one lane of a converged warp; keeps the surrounding code warp-uniform so ptxas can hold the
+// MMA descriptors in UNIFORM registers (an `if (lane == 0)` loop forces vector registers + R2UR moves before
+// every UTCHMMA: measured 150 cycles per MMA instead of 49).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -164,278 +189,493 @@ __device__ __forceinline__ __half f2h_sat(float x) {
     return __ushort_as_half(r);
 }
 
+// WN gate tanh(a) * sigmoid(b) (WN.cpp:85-98 via nn_tanh.cpp:6-21 and nn_sigmoid.cpp:3-7) with two
+// exponentials and one division: tanh(a) = sign(a) (1-u)/(1+u), u = e^{-2|a|}; sigmoid(b) = 1/(1+v), v = e^{-b}.
+// Mathematically identical to the reference's (e^a - e^-a)/(e^a + e^-a) * 1/(1 + e^-b), incl. its
+// saturation to +-1 / 0 for large arguments; differs by fp32 rounding only.
+__device__ __forceinline__ float gate_ref(float a, float b) {
+    const float u = expf(-2.0f * fabsf(a));
+    const float v = expf(-b);
+    const float num = copysignf(1.0f - u, a);
+    return num / ((1.0f + u) * (1.0f + v));
+}
+
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// split-fp16 activation planes
+// ---------------------------------------------------------------------------------------------
+struct Planes {            // device view of one activation tensor as hi|lo fp16 planes
+    __half* base = nullptr;  // hi: [C/8][rows_p][8]; lo follows at + (C/8)*rows_p*8 halves
+    int C = 0;
+    long long rows_p = 0;    // padded rows: sum(len) + 2*B*TC_GAP (+ slack)
+};
+__device__ __forceinline__ long long planes_row(const Seg& s, int u) { return (long long)seg_start(s, u) + (long long)(2 * u + 1) * TC_GAP; }
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x0 = v[2 * i] * TC_ASCALE, x1 = v[2 * i + 1] * TC_ASCALE;
+        const __half h0 = f2h_sat(x0), h1 = f2h_sat(x1);
+        const __half l0 = f2h_sat(x0 - __half2float(h0)), l1 = f2h_sat(x1 - __half2float(h1));
+        hh[i] = pack_h2(h0, h1);
+        ll[i] = pack_h2(l0, l1);
+    }
+    hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    lo = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+}
+
+// fp32 rows [T][C] (optionally through leaky-relu) -> planes, including the zero gap rows.
+// Used when the producer of a tensor is not a tensor-core conv (LayerNorm, attention, regulator ...).
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int ldx, Seg seg, int C, int in_act,
+                                                           float slope, Planes pl) {
+    const int u = blockIdx.y;
+    const int len = seg_len(seg, u);
+    const int seg0 = seg_start(seg, u);
+    const long long prow0 = planes_row(seg, u) - TC_GAP;
+    const int groups = C / 8;
+    const int rows = len + 2 * TC_GAP;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // row-major over (group, row): rows contiguous per group
+    if (idx >= rows * groups) return;
+    const int gq = idx / rows, r = idx - gq * rows;
+    const int tl = r - TC_GAP;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (tl >= 0 && tl < len) {
+        const float* src = x + (size_t)(seg0 + tl) * ldx + gq * 8;
+        const float4 q0 = *reinterpret_cast<const float4*>(src);
+        const float4 q1 = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        if (in_act == ACT_LEAKY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = v[i] < 0.f ? v[i] * slope : v[i];
+        }
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const size_t o = ((size_t)gq * pl.rows_p + (size_t)(prow0 + r)) * 8;
+    *reinterpret_cast<uint4*>(pl.base + o) = hi;
+    *reinterpret_cast<uint4*>(pl.base + (size_t)groups * pl.rows_p * 8 + o) = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel (v4: TMA-fed, software-pipelined)
+//
+// One CTA = one utterance x `tiles_per_cta` consecutive 128-row time tiles x one N-chunk (NC columns).
+// Work is a stream of "global chunks" g = (tile, K-chunk).  Four agents run concurrently:
+//   TMA lane (warp 6): activation box (hi, lo) of chunk g -> A[g % 2]
+//   producer (warp 5): weight stages through a ring, or loaded ONCE and kept resident when the layer's
+//                      packed weights for this N-chunk fit in shared memory
+//   MMA lane (warp 4): chunk g -> main[g&1] (accumulate = 0 at the chunk's first MMA), corr[tile&1]
+//   warps 0-3 / 4-7  : "set" s = tile & 1 owns TMEM main[s][2] + corr[s]: promotes each chunk's partial sum
+//                      into fp32 registers and runs the tile's epilogue, while the other set already
+//                      serves the next tile
+// so loads, MMAs, promotion and the epilogue of the previous tile all overlap
+// (TMEM: main[2][2] + corr[2] = 6*NC columns; one CTA per SM).
 // ---------------------------------------------------------------------------------------------
 struct TcP {
     const __half* wp;
     int NC, nchunks, kchunks, KC;
     float inv_scale;
-    int tmem_cols;   // power of two >= 32, >= NC
-    int rows_alloc;  // A tile rows incl. halo, == 2 (mod 8)
+    int tmem_cols;      // power of two >= 6*NC
+    int xr;             // A tile rows incl. halo (TMA box rows)
+    int tiles_per_cta;
+    int resident;       // 1: all kchunks*taps weight stages stay in smem for the CTA's lifetime
+    int nbstages;       // weight ring depth, or kchunks*taps when resident
+    int aring;          // activation ring depth (2..4)
+    int in_groups;      // Cin/8: lo plane starts at chunk coordinate in_groups
+    // optional split-fp16 outputs
+    Planes yp, y2p;
+    int out_act; float out_slope;
+    int write_f32;      // 0: planes only (p.y may be null)
+    long long* trace;   // optional clock64 trace of one CTA (tools/tc_trace.py): [5 roles][1024]
+    int dbg;            // timing experiments (STTS_TC_DBG): 1 = skip activation TMA after warm-up, 2 = skip epilogue stores
 };
 
+constexpr int TC_MAX_BSTAGES = 48;
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// store 8 consecutive channels (one 16-byte chunk) of one row into hi/lo planes
+__device__ __forceinline__ void planes_store8(const Planes& pl, long long prow, int ch0, const float* v) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const size_t o = ((size_t)(ch0 >> 3) * pl.rows_p + (size_t)prow) * 8;
+    *reinterpret_cast<uint4*>(pl.base + o) = hi;
+    *reinterpret_cast<uint4*>(pl.base + (size_t)(pl.C >> 3) * pl.rows_p * 8 + o) = lo;
+}
+
+#ifdef STTS_TC_TRACE_BUILD   // tools/tc_trace.py builds with this; production kernels carry no clock reads
+#define TC_TS(role, idx) do { if (tr && (idx) < 1024) tr[(role) * 1024 + (idx)] = clock64(); } while (0)
+#else
+#define TC_TS(role, idx) do { (void)tr; } while (0)
+#endif
+
 template <int NCT>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, const TcP t) {
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
+    constexpr int NC = NCT * 16;
     extern __shared__ __align__(128) uint8_t tsm[];
     const int u = blockIdx.y;
     const int seg0 = seg_start(p.seg, u);
     const int len = seg_len(p.seg, u);
-    const int t0 = blockIdx.x * 128;
-    if (t0 >= len) return;
+    const int ntiles_u = (len + 127) >> 7;
+    const int tile_b = blockIdx.x * t.tiles_per_cta;
+    if (tile_b >= ntiles_u) return;
+    const int NT = min(t.tiles_per_cta, ntiles_u - tile_b);
     const int nchunk = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NC = NCT * 16;
-    const int KC = t.KC, RA = t.rows_alloc;
-    const int halo = (p.k - 1) * p.dil;
-    const int XR = 128 + halo;
+    const int KC = t.KC, XR = t.xr, KCH = t.kchunks;
+    const int G = NT * KCH;               // global chunks of this CTA
+    const int NB = t.nbstages;
+    const long long prow_u = planes_row(p.seg, u);   // padded plane row of this utterance's row 0
+    long long* tr = (t.trace && blockIdx.x == 0 && blockIdx.y == (gridDim.y >> 1) && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? t.trace : nullptr;
 
     // ---- shared memory carve-up -------------------------------------------------------------
-    const uint32_t a_plane = (uint32_t)(KC / 8) * RA * 16;   // bytes per A plane
+    const uint32_t a_plane = (((uint32_t)(KC / 8) * XR * 16) + 127u) & ~127u;   // bytes per A plane (128B aligned)
+    const uint32_t a_buf = 2 * a_plane;                      // hi | lo
     const uint32_t b_plane = (uint32_t)KC * NC * 2;          // bytes per B plane
-    uint8_t* a_hi = tsm;
-    uint8_t* a_lo = tsm + a_plane;
-    uint8_t* bst = tsm + 2 * a_plane;                        // [STAGES][hi|lo]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bst + (size_t)TC_STAGES * 2 * b_plane);
-    uint64_t* b_full = bars;                  // [STAGES]
-    uint64_t* b_empty = bars + TC_STAGES;     // [STAGES]
-    uint64_t* a_full = bars + 2 * TC_STAGES;
-    uint64_t* a_empty = a_full + 1;
-    uint64_t* acc_full = a_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 3);
+    const uint32_t b_stage = 2 * b_plane;                    // hi | lo
+    const int AR = t.aring;
+    uint8_t* a_ring = tsm;                                   // [AR][hi|lo]
+    uint8_t* bst = tsm + (size_t)AR * a_buf;                 // [NB][hi|lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bst + (size_t)NB * b_stage);
+    uint64_t* a_full = bars;          // [TC_MAX_ARING]
+    uint64_t* a_empty = bars + 4;     // [TC_MAX_ARING]
+    uint64_t* m_full = bars + 8;      // [set][2] main accumulator written
+    uint64_t* m_empty = bars + 12;    // [set][2] main accumulator drained
+    uint64_t* c_full = bars + 16;     // [set] corr accumulator complete
+    uint64_t* c_empty = bars + 18;    // [set]
+    uint64_t* b_empty = bars + 20;    // [TC_MAX_RING]
+    uint64_t* b_full = bars + 20 + TC_MAX_RING;   // [NB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + NB);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [NC] bias (+ speaker vector) of this CTA's columns
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(a_full, 128);
-        mbar_init(a_empty, 1);
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < TC_MAX_ARING; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 128); }
+        for (int s = 0; s < TC_MAX_RING; ++s) mbar_init(&b_empty[s], 1);
+        for (int s = 0; s < NB; ++s) mbar_init(&b_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(t.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < NC) {
+        const int n = nchunk * NC + tid;
+        float b = 0.f;
+        if (n < p.Cout) {
+            if (p.bias) b = __ldg(p.bias + n);
+            if (p.gvec) b += __ldg(p.gvec + (size_t)u * p.ldg + n);
+        }
+        sbias[tid] = b;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const int nsteps = t.kchunks * p.k;  // weight stages consumed
+    const uint32_t tmem = *tmem_slot;     // main[s][b] @ (2s+b)*NC, corr[s] @ (4+s)*NC
 
-    if (warp < 4) {
-        // ================= A-tile loaders ====================================================
-        const bool xvec = ((p.ldx & 3) == 0) && ((((uintptr_t)p.x) & 15) == 0);
-        const int groups = KC / 8;
-        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+    if (warp < 8) {
+        // ================= promotion + epilogue ================================================
+        const int set = warp >> 2, wq = warp & 3;       // TMEM lane quarter = warp % 4
+        const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+        const float isc = t.inv_scale;
         float racc[NC];
+        const int ntl = (NT - set + 1) >> 1;            // tiles of this set: set, set+2, ...
+        for (int q = 0; q < ntl * KCH; ++q) {
+            const int jl = q / KCH, kc = q - jl * KCH, mb = q & 1;
+            const int tile = 2 * jl + set;
+            if (wq == 0) TC_TS(1 + set, q * 5 + 0);
+            mbar_wait(&m_full[set * 2 + mb], (q >> 1) & 1);      // this chunk's MMAs retired: main[set][mb] is final
+            tc_fence_after();
+            if (wq == 0) TC_TS(1 + set, q * 5 + 1);
+            const uint32_t tmain = tlane + (uint32_t)(set * 2 + mb) * NC;
+            if (kc == 0) {
 #pragma unroll
-        for (int j = 0; j < NC; ++j) racc[j] = 0.f;
-        for (int kc = 0; kc < t.kchunks; ++kc) {
-            if (kc > 0) {
-                mbar_wait(a_empty, (kc - 1) & 1);   // MMAs of the previous chunk retired: A is free, `main` is final
-                tc_fence_after();
-#pragma unroll
-                for (int cb = 0; cb < NC; cb += 16) {   // promote the chunk's hi*hi partial sum to fp32 registers
+                for (int cb = 0; cb < NC; cb += 16) {
                     float v[16];
-                    tc_ld16(tbase + cb, v);
+                    tc_ld16(tmain + cb, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[cb + j] = v[j];
+                }
+            } else {
+#pragma unroll
+                for (int cb = 0; cb < NC; cb += 16) {   // promote the chunk's hi*hi partial sum (round-to-nearest)
+                    float v[16];
+                    tc_ld16(tmain + cb, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
                 }
-                tc_fence_before();
             }
-            const int c0 = kc * KC;
-            for (int idx = tid; idx < XR * groups; idx += 128) {
-                const int r = idx / groups, g = idx % groups;
-                const int tl = t0 + r - p.padl;
-                float v[8];
+            tc_fence_before();
+            mbar_arrive(&m_empty[set * 2 + mb]);
+            if (wq == 0) TC_TS(1 + set, q * 5 + 2);
+            if (kc != KCH - 1) continue;
+            // ---------------- epilogue of tile `tile` -------------------------------------------
+            mbar_wait(&c_full[set], jl & 1);
+            tc_fence_after();
+            if (wq == 0) TC_TS(1 + set, q * 5 + 3);
+            const uint32_t tcorr = tlane + (uint32_t)(4 + set) * NC;
+            const int t0 = (tile_b + tile) * 128;
+            const int trow = t0 + wq * 32 + lane;
+            const bool rowok = trow < len;
+            const size_t row = (size_t)(seg0 + (rowok ? trow : 0));
+            const long long prow = prow_u + trow;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                if (tl >= 0 && tl < len) {
-                    const float* src = p.x + (size_t)(seg0 + tl) * p.ldx + c0 + g * 8;
-                    if (xvec) {
-                        const float4 q0 = *reinterpret_cast<const float4*>(src);
-                        const float4 q1 = *reinterpret_cast<const float4*>(src + 4);
-                        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            for (int cb = 0; cb < NC; cb += 16) {
+                float v[16];
+                tc_ld16(tcorr + cb, v);    // warp-collective: all lanes participate even for rows past the end
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = racc[cb + j] + v[j];
+                if (!rowok || (t.dbg & 2)) continue;
+                const int nb = nchunk * NC + cb;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], isc, sbias[cb + j]);
+                if (p.epi == EPI_GATE) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) o[j >> 1] = gate_ref(v[j], v[j + 1]);
+                    const int ob = nb >> 1;
+                    if (t.write_f32) {
+                        float* d = p.y + row * p.ldy + ob;
+                        if (nb + 15 < p.Cout && ((((uintptr_t)d) & 15) == 0)) {
+                            reinterpret_cast<float4*>(d)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                            reinterpret_cast<float4*>(d)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (nb + 2 * j + 1 < p.Cout) d[j] = o[j];
+                        }
+                    }
+                    if (t.yp.base && ob + 7 < t.yp.C) planes_store8(t.yp, prow, ob, o);
+                } else if (p.epi == EPI_RESSKIP) {
+                    // 16-column groups never straddle `split` (multiples of 16): x-update half or skip half
+                    const bool toX = nb < p.split;
+                    const int oc = toX ? nb : nb - p.split;
+                    float* d = toX ? p.y + row * p.ldy + oc : p.y2 + row * p.ldy2 + oc;
+                    const bool accum = toX || !p.y2_store;
+                    if (nb + 15 < p.Cout && ((p.split & 15) == 0) && ((((uintptr_t)d) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            if (accum) {
+                                const float4 o4 = reinterpret_cast<const float4*>(d)[q];
+                                w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
+                            }
+                            reinterpret_cast<float4*>(d)[q] = w4;
+                            v[4 * q] = w4.x; v[4 * q + 1] = w4.y; v[4 * q + 2] = w4.z; v[4 * q + 3] = w4.w;
+                        }
+                        const Planes& pl = toX ? t.yp : t.y2p;
+                        if (pl.base) { planes_store8(pl, prow, oc, v); planes_store8(pl, prow, oc + 8, v + 8); }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = src[i];
-                    }
-                    if (p.in_act == ACT_LEAKY) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = v[i] < 0.f ? v[i] * p.in_slope : v[i];
-                    }
-                }
-                uint32_t hh[4], ll[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float x0 = v[2 * i] * TC_ASCALE, x1 = v[2 * i + 1] * TC_ASCALE;
-                    const __half h0 = f2h_sat(x0), h1 = f2h_sat(x1);
-                    const __half l0 = f2h_sat(x0 - __half2float(h0)), l1 = f2h_sat(x1 - __half2float(h1));
-                    hh[i] = pack_h2(h0, h1);
-                    ll[i] = pack_h2(l0, l1);
-                }
-                const uint32_t off = (uint32_t)g * RA * 16 + (uint32_t)r * 16;
-                *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            }
-            fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(a_full);
-        }
-        // ================= epilogue ============================================================
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int trow = t0 + warp * 32 + lane;
-        const bool rowok = trow < len;
-        const size_t row = (size_t)(seg0 + (rowok ? trow : 0));
-        const float isc = t.inv_scale;
-#pragma unroll
-        for (int cb = 0; cb < NC; cb += 16) {
-            float v[16], c2[16];
-            tc_ld16(tbase + cb, v);    // warp-collective: all lanes participate even for rows past the end
-            tc_ld16(tbase + NC + cb, c2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (racc[cb + j] + v[j]) + c2[j];
-            if (!rowok) continue;
-            const int nb = nchunk * NC + cb;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = nb + j;
-                float b = 0.f;
-                if (n < p.Cout) {
-                    if (p.bias) b = __ldg(p.bias + n);
-                    if (p.gvec) b += __ldg(p.gvec + (size_t)u * p.ldg + n);
-                }
-                v[j] = v[j] * isc + b;
-            }
-            if (p.epi == EPI_GATE) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) o[j >> 1] = tanh_ref(v[j]) * sigmoid_ref(v[j + 1]);
-                float* d = p.y + row * p.ldy + (nb >> 1);
-                if (nb + 15 < p.Cout && ((((uintptr_t)d) & 15) == 0)) {
-                    reinterpret_cast<float4*>(d)[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    reinterpret_cast<float4*>(d)[1] = make_float4(o[4], o[5], o[6], o[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (nb + 2 * j + 1 < p.Cout) d[j] = o[j];
-                }
-            } else if (p.epi == EPI_RESSKIP) {
-                // 16-column groups never straddle `split` (multiples of 16): x-update half or skip half
-                const bool toX = nb < p.split;
-                float* d = toX ? p.y + row * p.ldy + nb : p.y2 + row * p.ldy2 + (nb - p.split);
-                const bool accum = toX || !p.y2_store;
-                if (nb + 15 < p.Cout && ((p.split & 15) == 0) && ((((uintptr_t)d) & 15) == 0)) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (accum) {
-                            const float4 o4 = reinterpret_cast<const float4*>(d)[q];
-                            w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = nb + j;
+                            if (n >= p.Cout) continue;
+                            if (n < p.split) {
+                                float* dd = p.y + row * p.ldy + n;
+                                *dd = *dd + v[j];
+                            } else {
+                                float* dd = p.y2 + row * p.ldy2 + (n - p.split);
+                                *dd = p.y2_store ? v[j] : (*dd + v[j]);
+                            }
                         }
-                        reinterpret_cast<float4*>(d)[q] = w4;
                     }
                 } else {
+                    float* d = t.write_f32 ? p.y + row * p.ldy + nb : nullptr;
+                    const float* rs = p.res ? p.res + row * p.ldr + nb : nullptr;
+                    const bool full = nb + 15 < p.Cout;
+                    const bool vec = full && (!d || ((((uintptr_t)d) & 15) == 0)) && (!rs || ((((uintptr_t)rs) & 15) == 0));
+                    if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = nb + j;
-                        if (n >= p.Cout) continue;
-                        if (n < p.split) {
-                            float* dd = p.y + row * p.ldy + n;
-                            *dd = *dd + v[j];
-                        } else {
-                            float* dd = p.y2 + row * p.ldy2 + (n - p.split);
-                            *dd = p.y2_store ? v[j] : (*dd + v[j]);
+                        for (int q = 0; q < 4; ++q) {
+                            float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            if (rs) { const float4 r4 = reinterpret_cast<const float4*>(rs)[q]; w4.x += r4.x; w4.y += r4.y; w4.z += r4.z; w4.w += r4.w; }
+                            if (p.epi == EPI_RELU) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
+                            else if (p.epi == EPI_ACCUM || p.epi == EPI_ACCUM_DIV) {
+                                const float4 o4 = reinterpret_cast<const float4*>(d)[q];
+                                w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
+                                if (p.epi == EPI_ACCUM_DIV) { w4.x /= p.div; w4.y /= p.div; w4.z /= p.div; w4.w /= p.div; }
+                            } else if (p.epi == EPI_TANH) { w4.x = tanh_ref(w4.x); w4.y = tanh_ref(w4.y); w4.z = tanh_ref(w4.z); w4.w = tanh_ref(w4.w); }
+                            if (d) reinterpret_cast<float4*>(d)[q] = w4;
+                            v[4 * q] = w4.x; v[4 * q + 1] = w4.y; v[4 * q + 2] = w4.z; v[4 * q + 3] = w4.w;
+                        }
+                        if (t.yp.base) {
+                            if (t.out_act == ACT_LEAKY) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * t.out_slope : v[j];
+                            }
+                            planes_store8(t.yp, prow, nb, v);
+                            planes_store8(t.yp, prow, nb + 8, v + 8);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (nb + j >= p.Cout) continue;
+                            float w1 = v[j];
+                            if (rs) w1 = w1 + rs[j];
+                            if (p.epi == EPI_RELU) w1 = w1 < 0.f ? 0.f : w1;
+                            else if (p.epi == EPI_ACCUM) w1 = d[j] + w1;
+                            else if (p.epi == EPI_ACCUM_DIV) w1 = (d[j] + w1) / p.div;
+                            else if (p.epi == EPI_TANH) w1 = tanh_ref(w1);
+                            if (d) d[j] = w1;
                         }
                     }
                 }
-            } else {
-                float* d = p.y + row * p.ldy + nb;
-                const float* rs = p.res ? p.res + row * p.ldr + nb : nullptr;
-                const bool full = nb + 15 < p.Cout;
-                const bool vec = full && ((((uintptr_t)d) & 15) == 0) && (!rs || ((((uintptr_t)rs) & 15) == 0));
-                if (vec) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (rs) { const float4 r4 = reinterpret_cast<const float4*>(rs)[q]; w4.x += r4.x; w4.y += r4.y; w4.z += r4.z; w4.w += r4.w; }
-                        if (p.epi == EPI_RELU) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
-                        else if (p.epi == EPI_ACCUM || p.epi == EPI_ACCUM_DIV) {
-                            const float4 o4 = reinterpret_cast<const float4*>(d)[q];
-                            w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
-                            if (p.epi == EPI_ACCUM_DIV) { w4.x /= p.div; w4.y /= p.div; w4.z /= p.div; w4.w /= p.div; }
-                        } else if (p.epi == EPI_TANH) { w4.x = tanh_ref(w4.x); w4.y = tanh_ref(w4.y); w4.z = tanh_ref(w4.z); w4.w = tanh_ref(w4.w); }
-                        reinterpret_cast<float4*>(d)[q] = w4;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (nb + j >= p.Cout) continue;
-                        float w1 = v[j];
-                        if (rs) w1 = w1 + rs[j];
-                        if (p.epi == EPI_RELU) w1 = w1 < 0.f ? 0.f : w1;
-                        else if (p.epi == EPI_ACCUM) w1 = d[j] + w1;
-                        else if (p.epi == EPI_ACCUM_DIV) w1 = (d[j] + w1) / p.div;
-                        else if (p.epi == EPI_TANH) w1 = tanh_ref(w1);
-                        d[j] = w1;
+            }
+            // zero the gap rows adjoining this utterance in the output planes (first / last tile only)
+            if (t.yp.base || t.y2p.base) {
+                const bool first = (tile_b + tile) == 0, last = (tile_b + tile) == ntiles_u - 1;
+                if (first || last) {
+                    const int tidl = wq * 32 + lane;
+                    for (int which = 0; which < 2; ++which) {
+                        const Planes& pl = which ? t.y2p : t.yp;
+                        if (!pl.base) continue;
+                        const int ocn = (p.epi == EPI_GATE) ? NC / 2 : NC;          // output channels of this CTA
+                        int oc0 = (p.epi == EPI_GATE) ? (nchunk * NC) >> 1 : nchunk * NC;
+                        if (p.epi == EPI_RESSKIP) {
+                            const bool toX = nchunk * NC < p.split;
+                            if (toX != (which == 0)) continue;
+                            if (!toX) oc0 -= p.split;
+                        } else if (which == 1) continue;
+                        const int ng = ocn / 8;
+                        const uint4 z = make_uint4(0, 0, 0, 0);
+                        for (int e = tidl; e < ng * TC_GAP * 2; e += 128) {
+                            const int side = e / (ng * TC_GAP), r2 = e - side * ng * TC_GAP;
+                            if ((side == 0 && !first) || (side == 1 && !last)) continue;
+                            const int gq = r2 / TC_GAP, rr = r2 - gq * TC_GAP;
+                            const int ch = oc0 + gq * 8;
+                            if (ch + 8 > pl.C) continue;
+                            const long long pr = side == 0 ? prow_u - TC_GAP + rr : prow_u + len + rr;
+                            const size_t o = ((size_t)(ch >> 3) * pl.rows_p + (size_t)pr) * 8;
+                            *reinterpret_cast<uint4*>(pl.base + o) = z;
+                            *reinterpret_cast<uint4*>(pl.base + (size_t)(pl.C >> 3) * pl.rows_p * 8 + o) = z;
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&c_empty[set]);
+            if (wq == 0) TC_TS(1 + set, q * 5 + 4);
         }
-        tc_fence_before();
-    } else if (warp == 4) {
-        // ================= MMA issuer (one elected lane) =======================================
-        if (lane == 0) {
+    } else if (warp == 8) {
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues) ==============
+        {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3, M>>4 (M = 128)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_s = smem_u32(bst);
-            const uint32_t a_lbo = (uint32_t)RA * 16, b_lbo = (uint32_t)NC * 16;
-            int step = 0;
-            uint32_t corr_acc = 0;
-            const uint32_t tmem_corr = tmem + NC;
-            for (int kc = 0; kc < t.kchunks; ++kc) {
-                mbar_wait(a_full, kc & 1);
+            const uint32_t a_s = smem_u32(a_ring), b_s = smem_u32(bst);
+            const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)NC * 16;
+            // descriptors are built once and only their 14-bit start-address field (units of 16 B) is advanced
+            // per MMA (no carry: smem < 256 KB)
+            const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+            const uint64_t b_bits = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+            const uint32_t a_k16 = (2 * a_lbo) >> 4, b_k16 = (2 * b_lbo) >> 4, b_lo_off = b_plane >> 4, a_lo_off = a_plane >> 4;
+            const int nk16 = KC / 16;
+            int bs = 0; uint32_t bph = 0;      // weight ring slot / phase
+            int buf = 0; uint32_t aph = 0;     // activation ring slot / phase
+            int tile = 0, kc = 0;
+            for (int g = 0; g < G; ++g) {
+                const int set = tile & 1, jl = tile >> 1, q = jl * KCH + kc, mb = q & 1;   // position in the set's own stream
+                TC_TS(0, g * 4 + 0);
+                mbar_wait_warp(&a_full[buf], aph);
+                TC_TS(0, g * 4 + 1);
+                if (q >= 2) mbar_wait_warp(&m_empty[set * 2 + mb], ((q >> 1) - 1) & 1);          // main[set][mb] drained
+                if (kc == 0 && jl >= 1) mbar_wait_warp(&c_empty[set], (jl - 1) & 1);             // corr[set] consumed by its epilogue
                 tc_fence_after();
-                uint32_t main_acc = 0;   // the previous chunk's partial sum was promoted to registers
-                for (int tap = 0; tap < p.k; ++tap, ++step) {
-                    const int s = step % TC_STAGES;
-                    mbar_wait(&b_full[s], (step / TC_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t bh = b_s + (uint32_t)s * 2 * b_plane, bl = bh + b_plane;
-                    const uint32_t shift = (uint32_t)(tap * p.dil) * 16;
-                    for (int k16 = 0; k16 < KC / 16; ++k16) {
-                        const uint64_t dah = tc_desc(a_hi_s + k16 * 2 * a_lbo + shift, a_lbo, 128);
-                        const uint64_t dal = tc_desc(a_lo_s + k16 * 2 * a_lbo + shift, a_lbo, 128);
-                        const uint64_t dbh = tc_desc(bh + k16 * 2 * b_lbo, b_lbo, 128);
-                        const uint64_t dbl = tc_desc(bl + k16 * 2 * b_lbo, b_lbo, 128);
-                        tc_mma_f16(tmem, dah, dbh, idesc, main_acc);
-                        main_acc = 1;
-                        tc_mma_f16(tmem_corr, dal, dbh, idesc, corr_acc);
-                        corr_acc = 1;
-                        tc_mma_f16(tmem_corr, dah, dbl, idesc, 1);
+                TC_TS(0, g * 4 + 2);
+                const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
+                const uint32_t tmain = tmem + (uint32_t)(set * 2 + mb) * NC, tcorr = tmem + (uint32_t)(4 + set) * NC;
+                uint32_t main_acc = 0;                 // the previous partial sum was promoted to registers
+                uint32_t corr_acc = kc == 0 ? 0u : 1u;
+                for (int tap = 0; tap < p.k; ++tap) {
+                    int s;
+                    if (t.resident) {
+                        s = kc * p.k + tap;
+                        if (tile == 0) { mbar_wait_warp(&b_full[s], 0); tc_fence_after(); }
+                    } else {
+                        s = bs;
+                        mbar_wait_warp(&b_full[s], bph);
+                        tc_fence_after();
+                        if (++bs == NB) { bs = 0; bph ^= 1; }
                     }
-                    tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
+                    uint64_t dah = dA0 + (uint32_t)(tap * p.dil);
+                    uint64_t dbh = b_bits | (uint64_t)(((b_s + (uint32_t)s * b_stage) & 0x3FFFFu) >> 4);
+                    for (int k16 = 0; k16 < nk16; ++k16) {
+                        if (elect_one()) {
+                            tc_mma_f16(tmain, dah, dbh, idesc, main_acc);
+                            tc_mma_f16(tcorr, dah + a_lo_off, dbh, idesc, corr_acc);
+                            tc_mma_f16(tcorr, dah, dbh + b_lo_off, idesc, 1);
+                        }
+                        main_acc = 1;
+                        corr_acc = 1;
+                        dah += a_k16;
+                        dbh += b_k16;
+                    }
+                    if (!t.resident && elect_one()) tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
                 }
-                tc_commit(a_empty);              // A tile may be overwritten
+                TC_TS(0, g * 4 + 3);
+                if (elect_one()) {
+                    tc_commit(&a_empty[buf]);              // A chunk may be overwritten
+                    tc_commit(&m_full[set * 2 + mb]);      // main[set][mb] holds this chunk's partial sum
+                    if (kc == KCH - 1) tc_commit(&c_full[set]);
+                }
+                __syncwarp();
+                if (++buf == AR) { buf = 0; aph ^= 1; }
+                if (++kc == KCH) { kc = 0; ++tile; }
             }
-            tc_commit(acc_full);
+        }
+    } else if (warp == 9) {
+        // ================= weight producer (bulk-copy engine) ==================================
+        if (lane == 0) {
+            const int per_tile = KCH * p.k;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(t.wp) + (size_t)nchunk * per_tile * b_stage;
+            if (t.resident) {
+                for (int s = 0; s < per_tile; ++s) {
+                    mbar_expect_tx(&b_full[s], b_stage);
+                    bulk_g2s(bst + (size_t)s * b_stage, src + (size_t)s * b_stage, b_stage, &b_full[s]);
+                }
+            } else {
+                const int nsteps = NT * per_tile;
+                int s = 0, off = 0; uint32_t ph = 1;   // first pass over the ring needs no wait
+                for (int step = 0; step < nsteps; ++step) {
+                    if (step >= NB) mbar_wait(&b_empty[s], ph);
+                    TC_TS(4, step);
+                    mbar_expect_tx(&b_full[s], b_stage);
+                    bulk_g2s(bst + (size_t)s * b_stage, src + (size_t)off * b_stage, b_stage, &b_full[s]);
+                    if (++s == NB) { s = 0; ph ^= 1; }
+                    if (++off == per_tile) off = 0;
+                }
+            }
         }
         __syncwarp();
     } else {
-        // ================= weight producer (bulk-copy engine) ==================================
+        // ================= activation producer (TMA) ===========================================
         if (lane == 0) {
-            const uint32_t stage_bytes = 2 * b_plane;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(t.wp) + (size_t)nchunk * nsteps * stage_bytes;
-            for (int step = 0; step < nsteps; ++step) {
-                const int s = step % TC_STAGES;
-                if (step >= TC_STAGES) mbar_wait(&b_empty[s], ((step / TC_STAGES) - 1) & 1);
-                mbar_expect_tx(&b_full[s], stage_bytes);
-                bulk_g2s(bst + (size_t)s * stage_bytes, src + (size_t)step * stage_bytes, stage_bytes, &b_full[s]);
+            const uint32_t box_bytes = (uint32_t)(KC / 8) * XR * 16;
+            int buf = 0, tile = 0, kc = 0; uint32_t ph = 1;
+            for (int g = 0; g < G; ++g) {
+                if (g >= AR) mbar_wait(&a_empty[buf], ph);   // MMAs of chunk g-AR retired
+                const long long r0 = prow_u + (long long)(tile_b + tile) * 128 - p.padl;   // >= 0: TC_GAP >= padl
+                uint8_t* dst = a_ring + (size_t)buf * a_buf;
+                if ((t.dbg & 1) && g >= AR) { mbar_arrive(&a_full[buf]); if (++buf == AR) { buf = 0; ph ^= 1; } if (++kc == KCH) { kc = 0; ++tile; } continue; }
+                TC_TS(3, g);
+                mbar_expect_tx(&a_full[buf], 2 * box_bytes);
+                tma_load_3d(dst, &amap, 0, (int)r0, kc * (KC / 8), &a_full[buf]);
+                tma_load_3d(dst + a_plane, &amap, 0, (int)r0, t.in_groups + kc * (KC / 8), &a_full[buf]);
+                if (++buf == AR) { buf = 0; ph ^= 1; }
+                if (++kc == KCH) { kc = 0; ++tile; }
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(t.tmem_cols));
     }
@@ -444,30 +684,93 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
 // ---------------------------------------------------------------------------------------------
 // host: eligibility + launch
 // ---------------------------------------------------------------------------------------------
-inline int tc_rows_alloc(int k, int dil) {
-    int r = 128 + (k - 1) * dil;
-    while ((r & 7) != 2) ++r;   // plane stride == 32 (mod 128) bytes: conflict-free 16 B stores across groups
-    return r;
-}
-inline size_t tc_smem_bytes(const TcWeights& w, int k, int dil) {
-    const size_t a = (size_t)2 * (w.KC / 8) * tc_rows_alloc(k, dil) * 16;
-    const size_t b = (size_t)TC_STAGES * 2 * w.KC * w.NC * 2;
-    return a + b + 128;
+struct TcPlan {
+    size_t smem;
+    int resident, nbstages, aring;
+};
+inline TcPlan tc_plan(const TcWeights& w, int k, int dil, bool want_resident) {
+    TcPlan pl;
+    const int xr = 128 + (k - 1) * dil;
+    const size_t a_plane = (((size_t)(w.KC / 8) * xr * 16) + 127) & ~size_t(127);
+    const size_t a_buf = 2 * a_plane;   // hi | lo
+    const size_t stage = (size_t)2 * w.KC * w.NC * 2;
+    const int per_tile = w.kchunks * k;
+    const size_t budget = 190 * 1024;   // one CTA per SM: use the shared memory for deep rings (latency hiding)
+    const size_t misc = (20 + TC_MAX_RING + TC_MAX_BSTAGES) * 8 + 16 + 64 * 4 + 128;
+    pl.aring = ((size_t)3 * a_buf + 4 * stage + misc <= budget) ? 3 : 2;
+    const size_t a = (size_t)pl.aring * a_buf;
+    pl.resident = (want_resident && per_tile <= TC_MAX_BSTAGES && a + stage * per_tile + misc <= budget) ? 1 : 0;
+    if (pl.resident) pl.nbstages = per_tile;
+    else {
+        size_t room = budget > a + misc ? (budget - a - misc) / stage : 2;
+        pl.nbstages = (int)std::max<size_t>(2, std::min<size_t>(6, room));
+    }
+    {   // tuning knobs (experiments): STTS_TC_AR = activation ring, STTS_TC_NB = weight ring, STTS_TC_RES = 0 disables residency
+        static const int e_ar = getenv("STTS_TC_AR") ? atoi(getenv("STTS_TC_AR")) : 0;
+        static const int e_nb = getenv("STTS_TC_NB") ? atoi(getenv("STTS_TC_NB")) : 0;
+        static const int e_res = getenv("STTS_TC_RES") ? atoi(getenv("STTS_TC_RES")) : -1;
+        if (e_ar >= 2 && e_ar <= TC_MAX_ARING) pl.aring = e_ar;
+        if (e_res == 0 && pl.resident) { pl.resident = 0; pl.nbstages = 4; }
+        if (e_nb >= 2 && e_nb <= TC_MAX_RING && !pl.resident) pl.nbstages = e_nb;
+        const size_t a2 = (size_t)pl.aring * a_buf;
+        pl.smem = a2 + stage * pl.nbstages + misc;
+        return pl;
+    }
 }
 inline bool tc_eligible(const TcWeights& w, const ConvP& p) {
     if (!w.ok) return false;
     if (p.Cin % 16 != 0 || p.Cout < 16) return false;
-    if (tc_smem_bytes(w, p.k, p.dil) > 200 * 1024) return false;
+    if ((p.k - 1) * p.dil > TC_GAP || p.padl > TC_GAP) return false;
+    if (128 + (p.k - 1) * p.dil > 256) return false;            // TMA box rows <= 256
+    if (tc_plan(w, p.k, p.dil, false).smem > 200 * 1024) return false;
     return true;
 }
-inline int tc_conv_launch(const TcWeights& w, const ConvP& p, int nseg, int maxlen, cudaStream_t stream) {
+struct TcOut {               // optional split-fp16 outputs requested from the epilogue
+    Planes yp, y2p;
+    int out_act = ACT_NONE; float out_slope = 0.f;
+    bool write_f32 = true;
+};
+// Encodes the 3D tensor map of an activation's planes: (8, rows_p, 2*C/8), box (8, xr, KC/8).
+inline bool tc_make_map(CUtensorMap* m, const Planes& in, int xr, int KC) {
+    cuuint64_t dims[3] = {8, (cuuint64_t)in.rows_p, (cuuint64_t)(2 * (in.C / 8))};
+    cuuint64_t strides[2] = {16, (cuuint64_t)in.rows_p * 16};
+    cuuint32_t box[3] = {8, (cuuint32_t)xr, (cuuint32_t)(KC / 8)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, in.base, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, const TcOut& out, int nseg, int maxlen,
+                          cudaStream_t stream) {
     TcP t;
     t.wp = w.packed; t.NC = w.NC; t.nchunks = w.nchunks; t.kchunks = w.kchunks; t.KC = w.KC; t.inv_scale = w.inv_scale;
     int cols = 32;
-    while (cols < 2 * w.NC) cols <<= 1;   // main + correction accumulators
+    while (cols < 6 * w.NC) cols <<= 1;   // main[2][2] + corr[2]
     t.tmem_cols = cols;
-    t.rows_alloc = tc_rows_alloc(p.k, p.dil);
-    const size_t sm = tc_smem_bytes(w, p.k, p.dil);
+    t.xr = 128 + (p.k - 1) * p.dil;
+    t.in_groups = in.C / 8;
+    t.yp = out.yp; t.y2p = out.y2p; t.out_act = out.out_act; t.out_slope = out.out_slope; t.write_f32 = out.write_f32 ? 1 : 0;
+    const int ntiles = (maxlen + 127) / 128;
+    // several tiles per CTA amortise TMEM allocation / barrier setup and let the epilogue of one tile hide
+    // behind the MMAs of the next; keep a grid of >= ~8 CTAs per SM when the problem allows it
+    // (one CTA per SM: 352 threads x 128 registers) -> the two epilogue sets alternate tiles inside the CTA
+    int tpc = std::min(ntiles, 8);
+    const long per_tile_ctas = (long)nseg * w.nchunks;
+    while (tpc > 2 && per_tile_ctas * ((ntiles + tpc - 1) / tpc) < 148L * 2) --tpc;
+    static const int env_tpc = getenv("STTS_TC_TPC") ? atoi(getenv("STTS_TC_TPC")) : 0;   // tuning knob
+    if (env_tpc > 0) tpc = std::min(env_tpc, std::max(1, ntiles));
+    t.tiles_per_cta = tpc;
+    static const int env_dbg = getenv("STTS_TC_DBG") ? atoi(getenv("STTS_TC_DBG")) : 0;
+    t.dbg = env_dbg;
+    static long long* trace_buf = nullptr;
+    static const int env_trace = getenv("STTS_TC_TRACE") ? atoi(getenv("STTS_TC_TRACE")) : 0;
+    if (env_trace && !trace_buf) { cudaMalloc(&trace_buf, 5 * 1024 * 8); }
+    if (env_trace) cudaMemsetAsync(trace_buf, 0, 5 * 1024 * 8, stream);
+    t.trace = env_trace ? trace_buf : nullptr;
+    const TcPlan pl = tc_plan(w, p.k, p.dil, tpc >= 2);
+    t.resident = pl.resident; t.nbstages = pl.nbstages; t.aring = pl.aring;
+    alignas(64) CUtensorMap amap;
+    if (!tc_make_map(&amap, in, t.xr, w.KC)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -476,12 +779,26 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, int nseg, int maxl
         cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dim3 g((maxlen + 127) / 128, nseg, w.nchunks);
+    dim3 g((ntiles + tpc - 1) / tpc, nseg, w.nchunks);
     switch (w.NC / 16) {
-        case 1: conv_tc_kernel<1><<<g, TC_THREADS, sm, stream>>>(p, t); break;
-        case 2: conv_tc_kernel<2><<<g, TC_THREADS, sm, stream>>>(p, t); break;
-        case 3: conv_tc_kernel<3><<<g, TC_THREADS, sm, stream>>>(p, t); break;
-        default: conv_tc_kernel<4><<<g, TC_THREADS, sm, stream>>>(p, t); break;
+        case 1: conv_tc_kernel<1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 2: conv_tc_kernel<2><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 3: conv_tc_kernel<3><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        default: conv_tc_kernel<4><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+    }
+    if (env_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
+        std::vector<long long> h(5 * 1024);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
+        static const char* names[5] = {"mma", "set0", "set1", "aprod", "bprod"};
+        fprintf(stderr, "TRACE grid=(%d,%d,%d) tpc=%d KCH=%d k=%d NC=%d KC=%d resident=%d nb=%d ar=%d\n", g.x, g.y, g.z, tpc, w.kchunks, p.k, w.NC, w.KC, pl.resident, pl.nbstages, pl.aring);
+        for (int r = 0; r < 5; ++r) {
+            fprintf(stderr, " %s:", names[r]);
+            for (int i = 0; i < 1024; ++i) if (h[r * 1024 + i]) fprintf(stderr, " %d:%lld", i, h[r * 1024 + i] - t0);
+            fprintf(stderr, "\n");
+        }
     }
     return 1;
 }

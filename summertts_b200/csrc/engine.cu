@@ -86,6 +86,13 @@ struct ConvOpts {
     float* y2 = nullptr; int ldy2 = 0;
     int split = 0, y2_store = 0;
     bool allow_tc = true;
+#ifdef STTS_WITH_TC
+    const Planes* in_planes = nullptr;   // input already available as split-fp16 planes (activation applied by its producer)
+    Planes* out_planes = nullptr;        // also emit y as planes (through out_act) for the next tensor-core conv
+    Planes* out2_planes = nullptr;       // EPI_RESSKIP: planes of the skip destination
+    int out_act = ACT_NONE; float out_slope = 0.f;
+    bool write_f32 = true;               // false: planes only (the fp32 tensor has no other reader)
+#endif
 };
 
 struct Arena {  // bump allocator over one device allocation
@@ -216,6 +223,31 @@ struct stts_engine {
     }
 
     // ---- helpers ---------------------------------------------------------------------------
+#ifdef STTS_WITH_TC
+    void* planeScratch = nullptr;
+    size_t planeScratchCap = 0;
+    static size_t planes_rows(int64_t rows_total, int nseg) { return (size_t)rows_total + (size_t)2 * nseg * TC_GAP + 256; }
+    static size_t planes_bytes(int64_t rows_total, int nseg, int C) { return planes_rows(rows_total, nseg) * (size_t)C * 4; }
+    Planes scratch_planes(int64_t rows_total, int nseg, int C) {
+        const size_t need = planes_bytes(rows_total, nseg, C);
+        if (need > planeScratchCap) {
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (planeScratch) CUDA_CHECK(cudaFree(planeScratch));
+            planeScratchCap = need + need / 2;
+            CUDA_CHECK(cudaMalloc(&planeScratch, planeScratchCap));
+        }
+        Planes pl;
+        pl.base = (__half*)planeScratch; pl.C = C; pl.rows_p = (long long)planes_rows(rows_total, nseg);
+        return pl;
+    }
+    Planes arena_planes(int64_t rows_total, int nseg, int C) {
+        Planes pl;
+        pl.C = C; pl.rows_p = (long long)planes_rows(rows_total, nseg);
+        pl.base = ws.get<__half>((size_t)pl.rows_p * C * 2);
+        return pl;
+    }
+    bool tc_layer(const DConv& c) const { return tensor_mode == 1 && c.tc.ok && (c.k - 1) * c.dil <= TC_GAP && c.padl <= TC_GAP; }
+#endif
     template <typename T>
     T* dalloc(size_t n) {
         void* p = nullptr;
@@ -366,11 +398,26 @@ struct stts_engine {
         p.y2_store = o.y2_store;
 #ifdef STTS_WITH_TC
         if (tensor_mode == 1 && o.allow_tc && tc_eligible(c.tc, p)) {
-            launches += tc_conv_launch(c.tc, p, nseg, maxlen, stream);
+            Planes in;
+            if (o.in_planes && o.in_planes->base) in = *o.in_planes;
+            else {   // the producer was not a tensor-core conv: split fp32 rows into planes here
+                in = scratch_planes(curRowsTotal, nseg, c.Cin);
+                dim3 g(((size_t)(maxlen + 2 * TC_GAP) * (c.Cin / 8) + 255) / 256, nseg);
+                split_planes_kernel<<<g, 256, 0, stream>>>(x, ldx, seg, c.Cin, o.in_act, o.in_slope, in);
+                launch_check();
+            }
+            TcOut out;
+            if (o.out_planes) out.yp = *o.out_planes;
+            if (o.out2_planes) out.y2p = *o.out2_planes;
+            out.out_act = o.out_act; out.out_slope = o.out_slope; out.write_f32 = o.write_f32;
+            const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream);
+            if (r < 0) throw CudaError("cuTensorMapEncodeTiled failed for an activation plane");
+            launches += r;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) throw CudaError(std::string("tc conv launch failed: ") + cudaGetErrorString(e));
             return;
         }
+        if (!o.write_f32 || o.in_planes) throw std::runtime_error("planes-only tensor routed to a non-tensor-core conv (planning bug)");
 #endif
         const int halo = (c.k - 1) * c.dil;
         if (c.Cout <= 8 && o.epi != EPI_GATE && o.epi != EPI_RESSKIP) {
@@ -688,7 +735,7 @@ void stts_engine::run() {
     size_t ffnW = 0, dpW = 0;
     for (auto& L : enc) ffnW = std::max<size_t>(ffnW, L.f1.Cout);
     dpW = durPredType == 1 ? (size_t)std::max(dp1.Cout, dp2.Cout) : (size_t)H;
-    size_t tokFloats = (size_t)Tt * (H * 5 + 3 * H + ffnW + inter + 3 * dpW + 64 + 8) + (size_t)B * (gin + 4096) + 4096;
+    size_t tokFloats = (size_t)Tt * (H * 5 + 3 * H + 2 * ffnW + inter + 3 * dpW + 64 + 8) + (size_t)B * (gin + 4096 + 2 * 64 * ffnW) + 512 * ffnW + 4096;
     ensure_ws(tokFloats * 4 + (1 << 20));
     ws.reset();
     float* x = ws.get<float>((size_t)Tt * H);
@@ -697,6 +744,10 @@ void stts_engine::run() {
     float* y = ws.get<float>((size_t)Tt * H);
     float* x1 = ws.get<float>((size_t)Tt * H);
     float* fh = ws.get<float>((size_t)Tt * ffnW);
+#ifdef STTS_WITH_TC
+    Planes encFhP;
+    if (tensor_mode == 1) encFhP = arena_planes(Tt, B, (int)ffnW);
+#endif
     float* mbuf = ws.get<float>((size_t)Tt * inter);
     float* logw = ws.get<float>((size_t)Tt);
     float* wceil = ws.get<float>((size_t)Tt);
@@ -748,8 +799,16 @@ void stts_engine::run() {
         conv(L.o, att, H, y, H, tseg, B, maxT);
         add_ln(x, y, L.n1, x1, Tt);
         ConvOpts r; r.epi = EPI_RELU;
+        ConvOpts r2;
+#ifdef STTS_WITH_TC
+        Planes fhP;
+        if (tc_layer(L.f1) && tc_layer(L.f2)) {   // relu(conv1) goes to conv2 as split-fp16 planes only
+            fhP = encFhP;
+            r.out_planes = &fhP; r.write_f32 = false; r2.in_planes = &fhP;
+        }
+#endif
         conv(L.f1, x1, H, fh, L.f1.Cout, tseg, B, maxT, r);
-        conv(L.f2, fh, L.f1.Cout, y, H, tseg, B, maxT);
+        conv(L.f2, fh, L.f1.Cout, y, H, tseg, B, maxT, r2);
         add_ln(x1, y, L.n2, x, Tt);
     }
     conv(encProj, x, H, mbuf, inter, tseg, B, maxT);
@@ -827,6 +886,7 @@ void stts_engine::run() {
     size_t need = tokEnd + 4096;
     const int WH = wnHidden;
     need += ((size_t)Ft * (inter * 2 + WH * 3)) * 4 + 8 * 256;
+    need += 3 * ((size_t)Ft + 2 * (size_t)B * 64 + 256) * WH * 4 + 4096;   // split-fp16 planes of h / acts / skip
     {
         size_t rows = Ft;
         need += rows * convPre.Cout * 4 + 256;
@@ -834,6 +894,7 @@ void stts_engine::run() {
         for (size_t i = 0; i < ups.size(); ++i) {
             rr *= upRates[i];
             need += ((size_t)Ft * rr * stageC[i] * 4 + 256) * 4;
+            need += 3 * (((size_t)Ft * rr + 2 * (size_t)B * 64 + 256) * stageC[i] * 4 + 256);   // planes xx / t1 / xa
         }
         if (decType != 0) {
             const size_t fr = (size_t)Ft * R + B;
@@ -863,6 +924,16 @@ void stts_engine::run() {
     float* hbuf = ws.get<float>((size_t)Ft * WH);
     float* acts = ws.get<float>((size_t)Ft * WH);
     float* skip = ws.get<float>((size_t)Ft * WH);
+#ifdef STTS_WITH_TC
+    Planes hP, actsP, skipP;
+    bool flowTc = tensor_mode == 1 && flowN > 0;
+    for (auto& L : flow) {
+        flowTc = flowTc && tc_layer(L.pre) && tc_layer(L.post);
+        for (auto& c : L.in) flowTc = flowTc && tc_layer(c);
+        for (auto& c : L.rs) flowTc = flowTc && tc_layer(c);
+    }
+    if (flowTc) { hP = arena_planes(Ft, B, WH); actsP = arena_planes(Ft, B, WH); skipP = arena_planes(Ft, B, WH); }
+#endif
 
     // ---- length regulator (expandM, SynthesizerTrn.cpp:304-321, :380-383) -----------------------
     {
@@ -881,20 +952,37 @@ void stts_engine::run() {
         const float* x0 = z + (parity ? half : 0);
         float* x1p = z + (parity ? 0 : half);
         curRowsTotal = Ft; curCls = STTS_CLS_FLOW_IO;
-        conv(L.pre, x0, inter, hbuf, WH, fseg, B, maxF);                        // h = pre(x0)
+        {
+            ConvOpts po;
+#ifdef STTS_WITH_TC
+            if (flowTc) po.out_planes = &hP;       // h feeds the k5 in-layer as planes
+#endif
+            conv(L.pre, x0, inter, hbuf, WH, fseg, B, maxF, po);                 // h = pre(x0)
+        }
         const int nl = (int)L.in.size();
         for (int l = 0; l < nl; ++l) {                                          // WN::forward, WN.cpp:100-149
             ConvOpts g; g.epi = EPI_GATE;
             if (L.hasCond) { g.gvec = gWn[i] + (size_t)l * 2 * WH; g.ldg = L.cond.Cout; }
             curCls = STTS_CLS_WN_IN;
-            conv(L.in[l], hbuf, WH, acts, WH, fseg, B, maxF, g);
             ConvOpts r; r.epi = EPI_RESSKIP; r.y2 = skip; r.ldy2 = WH; r.y2_store = (l == 0);
             r.split = (l < nl - 1) ? WH : 0;
+#ifdef STTS_WITH_TC
+            if (flowTc) {
+                g.in_planes = &hP; g.out_planes = &actsP; g.write_f32 = false;   // acts only ever feed res_skip
+                r.in_planes = &actsP;
+                if (l < nl - 1) r.out_planes = &hP;      // refreshed h for the next in-layer
+                else r.out2_planes = &skipP;             // finished skip sum feeds `post`
+            }
+#endif
+            conv(L.in[l], hbuf, WH, acts, WH, fseg, B, maxF, g);
             curCls = STTS_CLS_WN_RS;
             conv(L.rs[l], acts, WH, hbuf, WH, fseg, B, maxF, r);
         }
         ConvOpts a; a.epi = EPI_ACCUM;
         curCls = STTS_CLS_FLOW_IO;
+#ifdef STTS_WITH_TC
+        if (flowTc) a.in_planes = &skipP;
+#endif
         conv(L.post, skip, WH, x1p, inter, fseg, B, maxF, a);                   // x1 = x1 - post(h)
     }
     if (flowN % 2 == 1) {
@@ -929,15 +1017,39 @@ void stts_engine::run() {
         const Seg sseg{d_foff, rate, 0};
         curCls = STTS_CLS_DEC_RB; curRowsTotal = (int64_t)Ft * rate;
         const int ml = maxF * rate;
+#ifdef STTS_WITH_TC
+        Planes xxP, t1P, xaP;
+        bool rbTc = tensor_mode == 1;
+        for (int j = 0; j < nRbK; ++j) {
+            for (auto& c : rbs[s * nRbK + j].c1) rbTc = rbTc && tc_layer(c);
+            for (auto& c : rbs[s * nRbK + j].c2) rbTc = rbTc && tc_layer(c);
+        }
+        if (rbTc) {
+            xxP = arena_planes(curRowsTotal, B, C); t1P = arena_planes(curRowsTotal, B, C); xaP = arena_planes(curRowsTotal, B, C);
+            // leaky(0.1)(xx) once for the three ResBlock1 branches (ResBlock1.cpp:61)
+            dim3 g(((size_t)(ml + 2 * TC_GAP) * (C / 8) + 255) / 256, B);
+            split_planes_kernel<<<g, 256, 0, stream>>>(xx, C, sseg, C, ACT_LEAKY, 0.1f, xxP);
+            launch_check();
+        }
+#endif
         for (int j = 0; j < nRbK; ++j) {                                         // MRF: Generator_MS.cpp:177-196
             RB& rb = rbs[s * nRbK + j];
             const int nb = (int)rb.c1.size();
             for (int b = 0; b < nb; ++b) {                                       // ResBlock1::forward, ResBlock1.cpp:55-69
                 const float* src = b == 0 ? xx : xa;
                 ConvOpts o1; o1.in_act = ACT_LEAKY; o1.in_slope = 0.1f;
-                conv(rb.c1[b], src, C, t1, C, sseg, B, ml, o1);
                 ConvOpts o2; o2.in_act = ACT_LEAKY; o2.in_slope = 0.1f; o2.res = src; o2.ldr = C;
                 const bool last = b == nb - 1;
+#ifdef STTS_WITH_TC
+                if (rbTc) {
+                    o1.in_planes = b == 0 ? &xxP : &xaP;                                  // leaky(x) planes
+                    o1.out_planes = &t1P; o1.out_act = ACT_LEAKY; o1.out_slope = 0.1f;   // leaky(conv1(...)) planes only
+                    o1.write_f32 = false;
+                    o2.in_planes = &t1P;
+                    if (!last) { o2.out_planes = &xaP; o2.out_act = ACT_LEAKY; o2.out_slope = 0.1f; }
+                }
+#endif
+                conv(rb.c1[b], src, C, t1, C, sseg, B, ml, o1);
                 float* dst = xa;
                 if (last) {
                     dst = accb;
@@ -951,7 +1063,7 @@ void stts_engine::run() {
         cur = accb; curC = C;
     }
     float* o = ws.get<float>((size_t)std::max<int64_t>(St, 1));
-    curCls = STTS_CLS_DEC_TAIL; curRowsTotal = (int64_t)Ft * rate;
+    curCls = STTS_CLS_DEC_TAIL; curRowsTotal = (int64_t)Ft * rate + (decType == 0 ? 0 : B);
     if (decType == 0) {
         // leaky(0.01) -> conv_post -> tanh: Generator_hifigan.cpp:176-180
         ConvOpts t; t.in_act = ACT_LEAKY; t.in_slope = 0.01f; t.epi = EPI_TANH; t.allow_tc = false;
@@ -969,7 +1081,7 @@ void stts_engine::run() {
             launch_check();
         }
         conv(subPost, xr, curC, sp, subPost.Cout, sfr, B, maxF * rate + 1);
-        istft_frames_kernel<<<(frRows + 3) / 4, 256, 0, stream>>>(sp, subPost.Cout, frames, (int)frRows, subBands);
+        istft_frames_kernel<<<(frRows + 6) / 7, 256, 0, stream>>>(sp, subPost.Cout, frames, (int)frRows, subBands);
         launch_check();
         {
             dim3 g(((size_t)maxF * rate * 4 * subBands + 255) / 256, B);
@@ -1070,6 +1182,9 @@ void stts_destroy(stts_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void* p : e->owned) cudaFree(p);
+#ifdef STTS_WITH_TC
+    if (e->planeScratch) cudaFree(e->planeScratch);
+#endif
     if (e->wsAlloc) cudaFree(e->wsAlloc);
     for (void* p : {(void*)e->d_ids, (void*)e->d_toff, (void*)e->d_sids, (void*)e->d_ls, (void*)e->d_foff, (void*)e->d_nfr,
                     (void*)e->d_bseg, (void*)e->d_forced})
@@ -1259,6 +1374,7 @@ int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_float
         float* dy = e->dalloc<float>((size_t)outRows * outC);
         CUDA_CHECK(cudaMemset(dy, 0, (size_t)outRows * outC * 4));
         ConvOpts o; o.in_act = in_act; o.in_slope = slope; o.epi = epi;
+        e->curRowsTotal = T;
         e->conv(d, dx, r.inCh, dy, transposed ? d.Cout : outC, Seg{dso, 1, 0}, nseg, maxlen, o);
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
         *y = (float*)malloc((size_t)outRows * outC * 4);

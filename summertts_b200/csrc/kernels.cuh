@@ -724,27 +724,39 @@ __constant__ float c_sin16[16];
 // s: [rows][ldS] (bands * 18 columns), frames: [rows][bands*16].  4 rows per CTA, 64 threads per row.
 __global__ void __launch_bounds__(256) istft_frames_kernel(const float* __restrict__ s, int ldS,
                                                             float* __restrict__ frames, int rows, int bands) {
-    __shared__ float re[4][4][9], im[4][4][9];
-    const int rl = threadIdx.x >> 6, q = threadIdx.x & 63;
-    const int row = blockIdx.x * 4 + rl;
-    if (row < rows && q < bands * 9) {
-        const int b = q / 9, k = q % 9;
-        const float mag = expf(s[(size_t)row * ldS + b * 18 + k]);
-        const float ph = sinf(s[(size_t)row * ldS + b * 18 + 9 + k]) * 3.14159265358979323846f;
-        re[rl][b][k] = mag * cosf(ph);
-        im[rl][b][k] = mag * sinf(ph);
+    // 7 rows per CTA: phase 1 uses 7*36 = 252 threads (one per (row, band, bin)) for the transcendental
+    // work, phase 2 uses 64 threads per row for the 16-point inverse real DFT + window.
+    constexpr int RPB = 7;
+    __shared__ float re[RPB][4][9], im[RPB][4][9];
+    const int row0 = blockIdx.x * RPB;
+    {
+        const int rl = threadIdx.x / 36, q = threadIdx.x - rl * 36;
+        const int row = row0 + rl;
+        if (rl < RPB && row < rows && q < bands * 9) {
+            const int b = q / 9, k = q - b * 9;
+            const float mag = expf(s[(size_t)row * ldS + b * 18 + k]);
+            const float ph = sinf(s[(size_t)row * ldS + b * 18 + 9 + k]) * 3.14159265358979323846f;
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            re[rl][b][k] = mag * cs;
+            im[rl][b][k] = mag * sn;
+        }
     }
     __syncthreads();
-    if (row >= rows || q >= bands * 16) return;
-    const int b = q >> 4, n = q & 15;
-    float acc = 0.f;
+    for (int e = threadIdx.x; e < RPB * 64; e += 256) {
+        const int rl = e >> 6, q = e & 63;
+        const int row = row0 + rl;
+        if (row >= rows || q >= bands * 16) continue;
+        const int b = q >> 4, n = q & 15;
+        float acc = 0.f;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        const int mI = (k * n) & 15;
-        acc += re[rl][b][k] * c_cos16[mI] - im[rl][b][k] * c_sin16[mI];
+        for (int k = 1; k < 8; ++k) {
+            const int mI = (k * n) & 15;
+            acc += re[rl][b][k] * c_cos16[mI] - im[rl][b][k] * c_sin16[mI];
+        }
+        const float x = (re[rl][b][0] + ((n & 1) ? -re[rl][b][8] : re[rl][b][8]) + 2.0f * acc) * (1.0f / 16.0f);
+        frames[(size_t)row * (bands * 16) + q] = x * c_hann[n];
     }
-    const float x = (re[rl][b][0] + ((n & 1) ? -re[rl][b][8] : re[rl][b][8]) + 2.0f * acc) * (1.0f / 16.0f);
-    frames[(size_t)row * (bands * 16) + q] = x * c_hann[n];
 }
 
 // K12. overlap-add (hop 4) + window-sum normalisation + centre crop: iStft.cpp:99-123.
