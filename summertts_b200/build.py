@@ -33,7 +33,9 @@ def build_native(force: bool = False, verbose: bool = False, with_tc: bool | Non
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-o", LIB] + [os.path.join(CSRC, s) for s in SRCS]
     if with_tc:
-        cmd += ["-DSTTS_WITH_TC", "-lcuda"]
+        cmd += ["-DSTTS_WITH_TC"]
+    if os.environ.get("STTS_TRACE_BUILD", "0") == "1":
+        cmd += ["-DSTTS_TC_TRACE_BUILD"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

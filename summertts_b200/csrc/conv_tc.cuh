@@ -461,16 +461,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                     float* d = toX ? p.y + row * p.ldy + oc : p.y2 + row * p.ldy2 + oc;
                     const bool accum = toX || !p.y2_store;
                     if (nb + 15 < p.Cout && ((p.split & 15) == 0) && ((((uintptr_t)d) & 15) == 0)) {
+                        // phase-separated read-modify-write: all loads, then the adds, then all stores
+                        if (accum) {
+                            float4 o4[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            if (accum) {
-                                const float4 o4 = reinterpret_cast<const float4*>(d)[q];
-                                w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
+                            for (int q = 0; q < 4; ++q) o4[q] = __ldcg(reinterpret_cast<const float4*>(d) + q);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                v[4 * q] = o4[q].x + v[4 * q]; v[4 * q + 1] = o4[q].y + v[4 * q + 1];
+                                v[4 * q + 2] = o4[q].z + v[4 * q + 2]; v[4 * q + 3] = o4[q].w + v[4 * q + 3];
                             }
-                            reinterpret_cast<float4*>(d)[q] = w4;
-                            v[4 * q] = w4.x; v[4 * q + 1] = w4.y; v[4 * q + 2] = w4.z; v[4 * q + 3] = w4.w;
                         }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            __stcg(reinterpret_cast<float4*>(d) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                         const Planes& pl = toX ? t.yp : t.y2p;
                         if (pl.base) { planes_store8(pl, prow, oc, v); planes_store8(pl, prow, oc + 8, v + 8); }
                     } else {
@@ -736,9 +740,20 @@ inline bool tc_make_map(CUtensorMap* m, const Planes& in, int xr, int KC) {
     cuuint64_t strides[2] = {16, (cuuint64_t)in.rows_p * 16};
     cuuint32_t box[3] = {8, (cuuint32_t)xr, (cuuint32_t)(KC / 8)};
     cuuint32_t estr[3] = {1, 1, 1};
-    return cuTensorMapEncodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, in.base, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    // The driver entry point is resolved at run time (cudaGetDriverEntryPoint): the library has no link-time
+    // dependency on libcuda.so, so it still loads on a CPU-only host for the ABI / parser tests.
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return (EncodeFn)fn;
+    }();
+    if (!encode) return false;
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, const TcOut& out, int nseg, int maxlen,
                           cudaStream_t stream) {
@@ -764,9 +779,11 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     t.dbg = env_dbg;
     static long long* trace_buf = nullptr;
     static const int env_trace = getenv("STTS_TC_TRACE") ? atoi(getenv("STTS_TC_TRACE")) : 0;
-    if (env_trace && !trace_buf) { cudaMalloc(&trace_buf, 5 * 1024 * 8); }
-    if (env_trace) cudaMemsetAsync(trace_buf, 0, 5 * 1024 * 8, stream);
-    t.trace = env_trace ? trace_buf : nullptr;
+    static int trace_left = 2;
+    const bool do_trace = env_trace && (env_trace == 1 || (env_trace == 2 && p.epi == EPI_RESSKIP && trace_left > 0 && maxlen > 256));
+    if (do_trace && !trace_buf) { cudaMalloc(&trace_buf, 5 * 1024 * 8); }
+    if (do_trace) cudaMemsetAsync(trace_buf, 0, 5 * 1024 * 8, stream);
+    t.trace = do_trace ? trace_buf : nullptr;
     const TcPlan pl = tc_plan(w, p.k, p.dil, tpc >= 2);
     t.resident = pl.resident; t.nbstages = pl.nbstages; t.aring = pl.aring;
     alignas(64) CUtensorMap amap;
@@ -786,7 +803,8 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
         case 3: conv_tc_kernel<3><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
         default: conv_tc_kernel<4><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
     }
-    if (env_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
+    if (do_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
+        --trace_left;
         std::vector<long long> h(5 * 1024);
         cudaStreamSynchronize(stream);
         cudaMemcpy(h.data(), trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
