@@ -728,6 +728,10 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float* __restri
     // work, phase 2 uses 64 threads per row for the 16-point inverse real DFT + window.
     constexpr int RPB = 7;
     __shared__ float re[RPB][4][9], im[RPB][4][9];
+    // twiddle / window tables in SHARED memory: the index varies per lane, and divergent __constant__
+    // reads serialise (this kernel took 1.65 ms per step with constant-memory tables)
+    __shared__ float s_cos[16], s_sin[16], s_hann[16];
+    if (threadIdx.x < 16) { s_cos[threadIdx.x] = c_cos16[threadIdx.x]; s_sin[threadIdx.x] = c_sin16[threadIdx.x]; s_hann[threadIdx.x] = c_hann[threadIdx.x]; }
     const int row0 = blockIdx.x * RPB;
     {
         const int rl = threadIdx.x / 36, q = threadIdx.x - rl * 36;
@@ -752,16 +756,19 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float* __restri
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
             const int mI = (k * n) & 15;
-            acc += re[rl][b][k] * c_cos16[mI] - im[rl][b][k] * c_sin16[mI];
+            acc += re[rl][b][k] * s_cos[mI] - im[rl][b][k] * s_sin[mI];
         }
         const float x = (re[rl][b][0] + ((n & 1) ? -re[rl][b][8] : re[rl][b][8]) + 2.0f * acc) * (1.0f / 16.0f);
-        frames[(size_t)row * (bands * 16) + q] = x * c_hann[n];
+        frames[(size_t)row * (bands * 16) + q] = x * s_hann[n];
     }
 }
 
 // K12. overlap-add (hop 4) + window-sum normalisation + centre crop: iStft.cpp:99-123.
 // yb[i][b], i in [0, 4*(rows_u-1)) per utterance.  sfr: frame rows (len_u = 16F+1), sy: rate 4x.
 __global__ void istft_ola_kernel(const float* __restrict__ frames, float* __restrict__ yb, Seg sfr, Seg sy, int bands) {
+    __shared__ float s_hp[16];
+    if (threadIdx.x < 16) s_hp[threadIdx.x] = c_hann_pow[threadIdx.x];
+    __syncthreads();
     const int u = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nfr = seg_len(sfr, u);
@@ -778,7 +785,7 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, float* __rest
     for (int j = jlo; j <= jhi; ++j) {
         const int n = pos - 4 * j;
         acc += frames[(size_t)(f0 + j) * (bands * 16) + b * 16 + n];
-        ws += c_hann_pow[n];
+        ws += s_hp[n];
     }
     if (ws > 1e-14f) acc = acc / ws;
     yb[(size_t)(seg_start(sy, u) + i) * bands + b] = acc;
