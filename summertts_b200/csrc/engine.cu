@@ -655,6 +655,7 @@ void stts_engine::build(const Model& M) {
         }
     }
     if (isMS == 1) emg = upload(M.emg, (size_t)spkNum * gin);
+    CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // constant DFT tables
     float c16[16], s16[16];
     for (int i = 0; i < 16; ++i) { c16[i] = (float)std::cos(2.0 * M_PI * i / 16.0); s16[i] = (float)std::sin(2.0 * M_PI * i / 16.0); }
@@ -789,7 +790,7 @@ void stts_engine::run() {
         conv(L.qkv, x, H, qkv, 3 * H, tseg, B, maxT);
         {
             dim3 g((maxT + 15) / 16, nHeads, B);
-            size_t sm = ((size_t)16 * kc + 2 * 32 * (kc + 1) + 2 * relRows * kc + 16 * 16) * sizeof(float);
+            size_t sm = ((size_t)16 * kc + 2 * 32 * (kc + 4) + 2 * relRows * kc + 16 * 16) * sizeof(float);
             if (kc == 96) relattn_kernel<96><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
             else if (kc == 64) relattn_kernel<64><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
             else if (kc == 32) relattn_kernel<32><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);

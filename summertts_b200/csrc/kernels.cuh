@@ -329,8 +329,8 @@ template <int KC>
 __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                        const float* __restrict__ embK, const float* __restrict__ embV,
                                                        Seg seg, int C, int win, int relRows) {
-    constexpr int NL = KC / 32, KP = KC + 1, QT = 16;
-    extern __shared__ float sm[];
+    constexpr int NL = KC / 32, KP = KC + 4, QT = 16;   // KP % 4 == 0: float4 rows; 16*lane byte skew: conflict-free quarter-warps
+    extern __shared__ __align__(16) float sm[];
     float* qs = sm;                    // [QT][KC]
     float* ks = qs + QT * KC;          // [32][KP]
     float* vs = ks + 32 * KP;          // [32][KP]
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
         for (int c = 0; c < KC; ++c) s = fmaf(qs[r * KC + c], ek[d * KC + c], s);
         rk[r * 16 + d] = s;
     }
-    // per-warp state for its 4 queries
+    // per-warp state for its 4 queries (processed jointly: every K/V value read from smem feeds 4 FMAs)
     float m[4], l[4], acc[4][NL], sband[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -370,60 +370,74 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
 #pragma unroll
         for (int c = 0; c < NL; ++c) acc[a][c] = 0.f;
     }
+    const int qb = warp * 4;
     for (int j0 = 0; j0 < len; j0 += 32) {
         __syncthreads();
-        for (int i = tid; i < 32 * KC; i += 128) {
-            const int r = i / KC, c = i % KC;
+        for (int i = tid; i < 32 * (KC / 4); i += 128) {
+            const int r = i / (KC / 4), c4 = (i % (KC / 4)) * 4;
             const int t = j0 + r;
-            float kv = 0.f, vv = 0.f;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
             if (t < len) {
-                const float* src = qkv + (size_t)(seg0 + t) * ld + h * KC + c;
-                kv = src[C];
-                vv = src[2 * C];
+                const float* src = qkv + (size_t)(seg0 + t) * ld + h * KC + c4;
+                kv = *reinterpret_cast<const float4*>(src + C);
+                vv = *reinterpret_cast<const float4*>(src + 2 * C);
             }
-            ks[r * KP + c] = kv;
-            vs[r * KP + c] = vv;
+            *reinterpret_cast<float4*>(ks + r * KP + c4) = kv;
+            *reinterpret_cast<float4*>(vs + r * KP + c4) = vv;
         }
         __syncthreads();
         const int j = j0 + lane;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int c = 0; c < KC; c += 4) {
+            const float4 kv = *reinterpret_cast<const float4*>(ks + lane * KP + c);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 qv = *reinterpret_cast<const float4*>(qs + (qb + a) * KC + c);   // broadcast
+                s[a] = fmaf(qv.x, kv.x, s[a]); s[a] = fmaf(qv.y, kv.y, s[a]);
+                s[a] = fmaf(qv.z, kv.z, s[a]); s[a] = fmaf(qv.w, kv.w, s[a]);
+            }
+        }
+        float pj[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const int qi = warp * 4 + a;
-            const int i = q0 + qi;
-            if (i >= len) continue;  // warp-uniform
-            float s = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < KC; ++c) s = fmaf(qs[qi * KC + c], ks[lane * KP + c], s);
+            const int i = q0 + qb + a;
             const int d = j - i + win;
-            if (d >= 0 && d < R) s += rk[qi * 16 + d];
-            if (j >= len) s = -INFINITY;
-            // lane r keeps the raw score of relative offset r (j = i + r - win)
-            {
-                const int jr = i + lane - win;      // key this lane's band slot refers to
+            if (d >= 0 && d < R) s[a] += rk[(qb + a) * 16 + d];
+            if (j >= len) s[a] = -INFINITY;
+            {   // lane r keeps the raw score of relative offset r (key j = i + r - win)
+                const int jr = i + lane - win;
                 const int srcl = jr - j0;
-                const float got = __shfl_sync(0xffffffffu, s, srcl & 31);
-                if (lane < R && srcl >= 0 && srcl < 32 && jr >= 0 && jr < len) sband[a] = got;
+                const float got = __shfl_sync(0xffffffffu, s[a], srcl & 31);
+                if (lane < R && srcl >= 0 && srcl < 32 && jr >= 0 && jr < len && i < len) sband[a] = got;
             }
-            const float cm = warp_max(s);
+            const float cm = warp_max(s[a]);
             const float mn = fmaxf(m[a], cm);
             const float sc = expf(m[a] - mn);
-            const float pj = (j < len) ? expf(s - mn) : 0.f;
-            l[a] = l[a] * sc + warp_sum(pj);
+            pj[a] = (j < len) ? expf(s[a] - mn) : 0.f;
+            l[a] = l[a] * sc + warp_sum(pj[a]);
             m[a] = mn;
 #pragma unroll
             for (int c = 0; c < NL; ++c) acc[a][c] *= sc;
-            for (int jj = 0; jj < 32; ++jj) {
-                const float pb = __shfl_sync(0xffffffffu, pj, jj);
+        }
+#pragma unroll 4
+        for (int jj = 0; jj < 32; ++jj) {
+            float v[NL];
 #pragma unroll
-                for (int c = 0; c < NL; ++c) acc[a][c] = fmaf(pb, vs[jj * KP + lane + 32 * c], acc[a][c]);
+            for (int c = 0; c < NL; ++c) v[c] = vs[jj * KP + lane + 32 * c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float pb = __shfl_sync(0xffffffffu, pj[a], jj);
+#pragma unroll
+                for (int c = 0; c < NL; ++c) acc[a][c] = fmaf(pb, v[c], acc[a][c]);
             }
         }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const int qi = warp * 4 + a;
+        const int qi = qb + a;
         const int i = q0 + qi;
-        if (i >= len) continue;
+        if (i >= len) continue;   // warp-uniform
         // normalised band probabilities -> rel-v term
         float pb = 0.f;
         if (lane < R && sband[a] != -INFINITY) pb = expf(sband[a] - m[a]) / l[a];
