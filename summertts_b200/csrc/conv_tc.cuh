@@ -51,7 +51,7 @@ namespace stts {
 
 constexpr int TC_MAX_RING = 16;    // max weight ring depth (chosen per launch to fill shared memory)
 constexpr int TC_MAX_ARING = 4;    // max activation ring depth
-constexpr int TC_THREADS = 352;    // 2 x 4 promotion/epilogue warps (even / odd tiles) + MMA warp + weight-producer warp + activation-TMA warp
+constexpr int TC_THREADS = 384;    // 2 x 4 promotion/epilogue warps (even / odd tiles) + 2 MMA-issue warps (hi*hi | corrections) + weight-producer warp + activation-TMA warp
 constexpr int TC_GAP = 64;         // zero rows kept before/after every utterance in the fp16 planes (>= max conv halo)
 constexpr float TC_ASCALE = 8.0f;  // 2^3 activation pre-scale
 
@@ -358,10 +358,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [NC] bias (+ speaker vector) of this CTA's columns
 
     if (tid == 0) {
-        for (int i = 0; i < TC_MAX_ARING; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TC_MAX_ARING; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }   // both MMA warps release
         for (int i = 0; i < 4; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 128); }
-        for (int s = 0; s < TC_MAX_RING; ++s) mbar_init(&b_empty[s], 1);
+        for (int s = 0; s < TC_MAX_RING; ++s) mbar_init(&b_empty[s], 2);
         for (int s = 0; s < NB; ++s) mbar_init(&b_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -570,8 +570,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             mbar_arrive(&c_empty[set]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 4);
         }
-    } else if (warp == 8) {
-        // ================= MMA issuer (warp-uniform loop, one elected lane issues) ==============
+    } else if (warp == 8 || warp == 11) {
+        // ================= MMA issuers (warp-uniform loops, one elected lane issues) ============
+        // The instruction stream of the issuing thread, not the tensor pipe, limits small-N tiles (measured:
+        // ~150 cycles per MMA issued vs 53 executed), so the work is split: warp 8 issues the hi*hi MMAs into
+        // main[set][mb], warp 11 the two correction MMAs into corr[set].
+        const bool do_main = warp == 8;
         {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3, M>>4 (M = 128)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -591,8 +595,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 TC_TS(0, g * 4 + 0);
                 mbar_wait_warp(&a_full[buf], aph);
                 TC_TS(0, g * 4 + 1);
-                if (q >= 2) mbar_wait_warp(&m_empty[set * 2 + mb], ((q >> 1) - 1) & 1);          // main[set][mb] drained
-                if (kc == 0 && jl >= 1) mbar_wait_warp(&c_empty[set], (jl - 1) & 1);             // corr[set] consumed by its epilogue
+                if (do_main) { if (q >= 2) mbar_wait_warp(&m_empty[set * 2 + mb], ((q >> 1) - 1) & 1); }          // main[set][mb] drained
+                else if (kc == 0 && jl >= 1) mbar_wait_warp(&c_empty[set], (jl - 1) & 1);                       // corr[set] consumed by its epilogue
                 tc_fence_after();
                 TC_TS(0, g * 4 + 2);
                 const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
@@ -610,26 +614,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                         tc_fence_after();
                         if (++bs == NB) { bs = 0; bph ^= 1; }
                     }
-                    uint64_t dah = dA0 + (uint32_t)(tap * p.dil);
-                    uint64_t dbh = b_bits | (uint64_t)(((b_s + (uint32_t)s * b_stage) & 0x3FFFFu) >> 4);
-                    for (int k16 = 0; k16 < nk16; ++k16) {
-                        if (elect_one()) {
-                            tc_mma_f16(tmain, dah, dbh, idesc, main_acc);
-                            tc_mma_f16(tcorr, dah + a_lo_off, dbh, idesc, corr_acc);
-                            tc_mma_f16(tcorr, dah, dbh + b_lo_off, idesc, 1);
+                    const uint64_t dah = dA0 + (uint32_t)(tap * p.dil);
+                    const uint64_t dbh = b_bits | (uint64_t)(((b_s + (uint32_t)s * b_stage) & 0x3FFFFu) >> 4);
+                    if (elect_one()) {   // one election per tap: all MMAs of the stage issue back-to-back
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16) {
+                            if (k16 < nk16) {
+                                const uint64_t a = dah + (uint32_t)(k16 * a_k16), b = dbh + (uint32_t)(k16 * b_k16);
+                                if (do_main) tc_mma_f16(tmain, a, b, idesc, k16 == 0 ? main_acc : 1u);
+                                else {
+                                    tc_mma_f16(tcorr, a + a_lo_off, b, idesc, k16 == 0 ? corr_acc : 1u);
+                                    tc_mma_f16(tcorr, a, b + b_lo_off, idesc, 1);
+                                }
+                            }
                         }
-                        main_acc = 1;
-                        corr_acc = 1;
-                        dah += a_k16;
-                        dbh += b_k16;
+                        if (!t.resident) tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
                     }
-                    if (!t.resident && elect_one()) tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
+                    main_acc = 1;
+                    corr_acc = 1;
                 }
                 TC_TS(0, g * 4 + 3);
                 if (elect_one()) {
-                    tc_commit(&a_empty[buf]);              // A chunk may be overwritten
-                    tc_commit(&m_full[set * 2 + mb]);      // main[set][mb] holds this chunk's partial sum
-                    if (kc == KCH - 1) tc_commit(&c_full[set]);
+                    tc_commit(&a_empty[buf]);              // A chunk may be overwritten (needs both issuers)
+                    if (do_main) tc_commit(&m_full[set * 2 + mb]);      // main[set][mb] holds this chunk's partial sum
+                    else if (kc == KCH - 1) tc_commit(&c_full[set]);
                 }
                 __syncwarp();
                 if (++buf == AR) { buf = 0; aph ^= 1; }
