@@ -190,3 +190,20 @@ def test_native_kernels_ran(native_lib, fast_blob):
     t = E.last_timing()
     assert t["total"] > 0 and t["flow"] > 0 and t["dec"] > 0
     E.close()
+
+
+def test_tensor_path_matches_ffma_path(native_lib, fast_blob):
+    """The tcgen05 split-fp16 path (planes handed from conv to conv, TMA-fed) and the fp32 FFMA tiles are two
+    implementations of the same convs: same sample counts, waveforms within the fp32 noise of the stack."""
+    rng = np.random.default_rng(21)
+    utts = [synth_ids(rng, n) for n in (40, 7, 96)]
+    E = engine.SynthesizerTrn(fast_blob)
+    E.set_forced_durations(np.full(sum(len(u) for u in utts), 3.0, np.float32))
+    E.set_tensor_path(1)
+    a = E.infer_batch(utts)
+    E.set_tensor_path(0)
+    b = E.infer_batch(utts)
+    for x, y in zip(a, b):
+        assert x.size == y.size
+        assert np.abs(x.astype(np.int64) - y.astype(np.int64)).max() <= 4
+    E.close()
