@@ -57,7 +57,8 @@ constexpr float TC_ASCALE = 8.0f;  // 2^3 activation pre-scale
 
 struct TcWeights {
     __half* packed = nullptr;  // [nchunks][kchunks][taps][plane hi,lo][KC/8][NC][8]
-    int NC = 0;                // accumulator columns per CTA (multiple of 16, <= 64)
+    int NC = 0;                // accumulator columns per CTA (multiple of 16; <= 64, or 128 in column-split mode)
+    int colsplit = 0;          // 1: 128 columns per CTA, the two epilogue sets own 64 columns each of EVERY tile
     int nchunks = 0, kchunks = 0, KC = 0, taps = 0;
     float inv_scale = 1.f;     // 2^-(k+3): applied to the accumulator in the epilogue
     bool ok = false;
@@ -76,7 +77,13 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     const int KC = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
     const int Cr = (Cout + 15) & ~15;
     int NC = Cr;
-    if (Cr > 64) {  // split into equal chunks of <= 64 columns (multiple of 16): 64 fp32 register accumulators/thread
+    t.colsplit = 0;
+    static const int env_cs = getenv("STTS_TC_COLSPLIT") ? atoi(getenv("STTS_TC_COLSPLIT")) : 1;
+    if (Cout >= 128 && KC == 64 && env_cs) {
+        // wide layers: N = 128 MMAs (65 cycles each instead of 2 x 53, half the MMA count and A-tile traffic)
+        NC = 128;
+        t.colsplit = 1;
+    } else if (Cr > 64) {  // split into equal chunks of <= 64 columns (multiple of 16): 64 fp32 register accumulators/thread
         int n = (Cr + 63) / 64;
         NC = (((Cr + n - 1) / n) + 15) & ~15;
     }
@@ -285,6 +292,7 @@ struct TcP {
     int resident;       // 1: all kchunks*taps weight stages stay in smem for the CTA's lifetime
     int nbstages;       // weight ring depth, or kchunks*taps when resident
     int aring;          // activation ring depth (2..4)
+    int colsplit;       // 1: CTA = 2*NC columns, set s owns columns [s*NC, (s+1)*NC) of every tile
     int in_groups;      // Cin/8: lo plane starts at chunk coordinate in_groups
     // optional split-fp16 outputs
     Planes yp, y2p;
@@ -318,7 +326,7 @@ __device__ __forceinline__ void planes_store8(const Planes& pl, long long prow, 
 #define TC_TS(role, idx) do { (void)tr; } while (0)
 #endif
 
-template <int NCT>
+template <int NCT, int CS>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
     constexpr int NC = NCT * 16;
     extern __shared__ __align__(128) uint8_t tsm[];
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
     const int nchunk = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = t.KC, XR = t.xr, KCH = t.kchunks;
+    constexpr int NCW = CS ? 2 * NC : NC;     // columns of this CTA (MMA N)
     const int G = NT * KCH;               // global chunks of this CTA
     const int NB = t.nbstages;
     const long long prow_u = planes_row(p.seg, u);   // padded plane row of this utterance's row 0
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
     // ---- shared memory carve-up -------------------------------------------------------------
     const uint32_t a_plane = (((uint32_t)(KC / 8) * XR * 16) + 127u) & ~127u;   // bytes per A plane (128B aligned)
     const uint32_t a_buf = 2 * a_plane;                      // hi | lo
-    const uint32_t b_plane = (uint32_t)KC * NC * 2;          // bytes per B plane
+    const uint32_t b_plane = (uint32_t)KC * NCW * 2;         // bytes per B plane
     const uint32_t b_stage = 2 * b_plane;                    // hi | lo
     const int AR = t.aring;
     uint8_t* a_ring = tsm;                                   // [AR][hi|lo]
@@ -359,8 +368,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
 
     if (tid == 0) {
         for (int i = 0; i < TC_MAX_ARING; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }   // both MMA warps release
-        for (int i = 0; i < 4; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 128); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], CS ? 256 : 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], CS ? 256 : 128); }
         for (int s = 0; s < TC_MAX_RING; ++s) mbar_init(&b_empty[s], 2);
         for (int s = 0; s < NB; ++s) mbar_init(&b_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -369,8 +378,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(t.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < NC) {
-        const int n = nchunk * NC + tid;
+    if (tid < NCW) {
+        const int n = nchunk * NCW + tid;
         float b = 0.f;
         if (n < p.Cout) {
             if (p.bias) b = __ldg(p.bias + n);
@@ -389,15 +398,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
         const float isc = t.inv_scale;
         float racc[NC];
-        const int ntl = (NT - set + 1) >> 1;            // tiles of this set: set, set+2, ...
-        for (int q = 0; q < ntl * KCH; ++q) {
+        // alternating mode: set s serves tiles s, s+2, ... with its own main[s][2] / corr[s];
+        // column-split mode: both sets serve every tile, set s owns columns [s*NC, (s+1)*NC) of main[2] / corr[2]
+        const int ntl = (NT - set + 1) >> 1;
+        const int nq = CS ? G : ntl * KCH;
+        const int ccol = CS ? set * NC : 0;             // this set's first column inside the CTA's column block
+        for (int q = 0; q < nq; ++q) {
             const int jl = q / KCH, kc = q - jl * KCH, mb = q & 1;
-            const int tile = 2 * jl + set;
+            const int tile = CS ? jl : 2 * jl + set;
+            const int mi = CS ? mb : set * 2 + mb;       // main accumulator / barrier index
             if (wq == 0) TC_TS(1 + set, q * 5 + 0);
-            mbar_wait(&m_full[set * 2 + mb], (q >> 1) & 1);      // this chunk's MMAs retired: main[set][mb] is final
+            mbar_wait(&m_full[mi], (q >> 1) & 1);        // this chunk's MMAs retired: the main accumulator is final
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 1);
-            const uint32_t tmain = tlane + (uint32_t)(set * 2 + mb) * NC;
+            const uint32_t tmain = tlane + (CS ? (uint32_t)(mb * 2 * NC + ccol) : (uint32_t)(set * 2 + mb) * NC);
             if (kc == 0) {
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += 16) {
@@ -416,14 +430,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(&m_empty[set * 2 + mb]);
+            mbar_arrive(&m_empty[mi]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 2);
             if (kc != KCH - 1) continue;
             // ---------------- epilogue of tile `tile` -------------------------------------------
-            mbar_wait(&c_full[set], jl & 1);
+            const int ci = CS ? (tile & 1) : set;        // corr accumulator / barrier index
+            mbar_wait(&c_full[ci], CS ? ((tile >> 1) & 1) : (jl & 1));
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 3);
-            const uint32_t tcorr = tlane + (uint32_t)(4 + set) * NC;
+            const uint32_t tcorr = tlane + (CS ? (uint32_t)(4 * NC + ci * 2 * NC + ccol) : (uint32_t)(4 + set) * NC);
             const int t0 = (tile_b + tile) * 128;
             const int trow = t0 + wq * 32 + lane;
             const bool rowok = trow < len;
@@ -436,9 +451,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = racc[cb + j] + v[j];
                 if (!rowok || (t.dbg & 2)) continue;
-                const int nb = nchunk * NC + cb;
+                const int nb = nchunk * NCW + ccol + cb;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], isc, sbias[cb + j]);
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], isc, sbias[ccol + cb + j]);
                 if (p.epi == EPI_GATE) {
                     float o[8];
 #pragma unroll
@@ -544,9 +559,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                         const Planes& pl = which ? t.y2p : t.yp;
                         if (!pl.base) continue;
                         const int ocn = (p.epi == EPI_GATE) ? NC / 2 : NC;          // output channels of this CTA
-                        int oc0 = (p.epi == EPI_GATE) ? (nchunk * NC) >> 1 : nchunk * NC;
+                        int oc0 = (p.epi == EPI_GATE) ? (nchunk * NCW + ccol) >> 1 : nchunk * NCW + ccol;
                         if (p.epi == EPI_RESSKIP) {
-                            const bool toX = nchunk * NC < p.split;
+                            const bool toX = nchunk * NCW + ccol < p.split;
                             if (toX != (which == 0)) continue;
                             if (!toX) oc0 -= p.split;
                         } else if (which == 1) continue;
@@ -567,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 }
             }
             tc_fence_before();
-            mbar_arrive(&c_empty[set]);
+            mbar_arrive(&c_empty[ci]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 4);
         }
     } else if (warp == 8 || warp == 11) {
@@ -578,9 +593,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         const bool do_main = warp == 8;
         {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3, M>>4 (M = 128)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a_s = smem_u32(a_ring), b_s = smem_u32(bst);
-            const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)NC * 16;
+            const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)NCW * 16;
             // descriptors are built once and only their 14-bit start-address field (units of 16 B) is advanced
             // per MMA (no carry: smem < 256 KB)
             const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
@@ -591,16 +606,21 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             int buf = 0; uint32_t aph = 0;     // activation ring slot / phase
             int tile = 0, kc = 0;
             for (int g = 0; g < G; ++g) {
-                const int set = tile & 1, jl = tile >> 1, q = jl * KCH + kc, mb = q & 1;   // position in the set's own stream
+                const int set = tile & 1, jl = tile >> 1;
+                const int q = CS ? g : jl * KCH + kc;      // position in the accumulator stream (per set when alternating)
+                const int mb = q & 1;
+                const int mi = CS ? mb : set * 2 + mb, ci = CS ? (tile & 1) : set;
                 TC_TS(0, g * 4 + 0);
                 mbar_wait_warp(&a_full[buf], aph);
                 TC_TS(0, g * 4 + 1);
-                if (do_main) { if (q >= 2) mbar_wait_warp(&m_empty[set * 2 + mb], ((q >> 1) - 1) & 1); }          // main[set][mb] drained
-                else if (kc == 0 && jl >= 1) mbar_wait_warp(&c_empty[set], (jl - 1) & 1);                       // corr[set] consumed by its epilogue
+                if (do_main) { if (q >= 2) mbar_wait_warp(&m_empty[mi], ((q >> 1) - 1) & 1); }                   // main accumulator drained
+                else if (kc == 0 && (CS ? tile >= 2 : jl >= 1))                                                  // corr accumulator consumed by its epilogue
+                    mbar_wait_warp(&c_empty[ci], CS ? (((tile >> 1) - 1) & 1) : ((jl - 1) & 1));
                 tc_fence_after();
                 TC_TS(0, g * 4 + 2);
                 const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
-                const uint32_t tmain = tmem + (uint32_t)(set * 2 + mb) * NC, tcorr = tmem + (uint32_t)(4 + set) * NC;
+                const uint32_t tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (uint32_t)(set * 2 + mb) * NC);
+                const uint32_t tcorr = tmem + (CS ? (uint32_t)(4 * NC + ci * 2 * NC) : (uint32_t)(4 + set) * NC);
                 uint32_t main_acc = 0;                 // the previous partial sum was promoted to registers
                 uint32_t corr_acc = kc == 0 ? 0u : 1u;
                 for (int tap = 0; tap < p.k; ++tap) {
@@ -636,8 +656,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 TC_TS(0, g * 4 + 3);
                 if (elect_one()) {
                     tc_commit(&a_empty[buf]);              // A chunk may be overwritten (needs both issuers)
-                    if (do_main) tc_commit(&m_full[set * 2 + mb]);      // main[set][mb] holds this chunk's partial sum
-                    else if (kc == KCH - 1) tc_commit(&c_full[set]);
+                    if (do_main) tc_commit(&m_full[mi]);      // the main accumulator holds this chunk's partial sum
+                    else if (kc == KCH - 1) tc_commit(&c_full[ci]);
                 }
                 __syncwarp();
                 if (++buf == AR) { buf = 0; aph ^= 1; }
@@ -710,7 +730,7 @@ inline TcPlan tc_plan(const TcWeights& w, int k, int dil, bool want_resident) {
     const size_t stage = (size_t)2 * w.KC * w.NC * 2;
     const int per_tile = w.kchunks * k;
     const size_t budget = 190 * 1024;   // one CTA per SM: use the shared memory for deep rings (latency hiding)
-    const size_t misc = (20 + TC_MAX_RING + TC_MAX_BSTAGES) * 8 + 16 + 64 * 4 + 128;
+    const size_t misc = (20 + TC_MAX_RING + TC_MAX_BSTAGES) * 8 + 16 + 128 * 4 + 128;
     pl.aring = ((size_t)3 * a_buf + 4 * stage + misc <= budget) ? 3 : 2;
     const size_t a = (size_t)pl.aring * a_buf;
     pl.resident = (want_resident && per_tile <= TC_MAX_BSTAGES && a + stage * per_tile + misc <= budget) ? 1 : 0;
@@ -770,7 +790,7 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     TcP t;
     t.wp = w.packed; t.NC = w.NC; t.nchunks = w.nchunks; t.kchunks = w.kchunks; t.KC = w.KC; t.inv_scale = w.inv_scale;
     int cols = 32;
-    while (cols < 6 * w.NC) cols <<= 1;   // main[2][2] + corr[2]
+    while (cols < (w.colsplit ? 512 : 6 * w.NC)) cols <<= 1;   // main[2][2] + corr[2]  (column-split: main[2] + corr[2], 128 wide)
     t.tmem_cols = cols;
     t.xr = 128 + (p.k - 1) * p.dil;
     t.in_groups = in.C / 8;
@@ -796,22 +816,25 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     t.trace = do_trace ? trace_buf : nullptr;
     const TcPlan pl = tc_plan(w, p.k, p.dil, tpc >= 2);
     t.resident = pl.resident; t.nbstages = pl.nbstages; t.aring = pl.aring;
+    t.colsplit = w.colsplit;
     alignas(64) CUtensorMap amap;
     if (!tc_make_map(&amap, in, t.xr, w.KC)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     dim3 g((ntiles + tpc - 1) / tpc, nseg, w.nchunks);
-    switch (w.NC / 16) {
-        case 1: conv_tc_kernel<1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 2: conv_tc_kernel<2><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 3: conv_tc_kernel<3><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        default: conv_tc_kernel<4><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+    if (w.colsplit) conv_tc_kernel<4, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap);
+    else switch (w.NC / 16) {
+        case 1: conv_tc_kernel<1, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 2: conv_tc_kernel<2, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 3: conv_tc_kernel<3, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        default: conv_tc_kernel<4, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
     }
     if (do_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
         --trace_left;
