@@ -59,6 +59,7 @@ struct TcWeights {
     __half* packed = nullptr;  // [nchunks][kchunks][taps][plane hi,lo][KC/8][NC][8]
     int NC = 0;                // accumulator columns per CTA (multiple of 16; <= 64, or 128 in column-split mode)
     int colsplit = 0;          // 1: 128 columns per CTA, the two epilogue sets own 64 columns each of EVERY tile
+    int merge = 0;             // 1 (single K-chunk layers): stage = [c8][hi rows | lo rows][8]; one N=2*NC MMA does hi*hi and hi*lo
     int nchunks = 0, kchunks = 0, KC = 0, taps = 0;
     float inv_scale = 1.f;     // 2^-(k+3): applied to the accumulator in the epilogue
     bool ok = false;
@@ -88,6 +89,8 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
         NC = (((Cr + n - 1) / n) + 15) & ~15;
     }
     t.NC = NC; t.nchunks = (Cr + NC - 1) / NC; t.KC = KC; t.kchunks = Cin / KC; t.taps = k;
+    static const int env_mg = getenv("STTS_TC_MERGE") ? atoi(getenv("STTS_TC_MERGE")) : 1;
+    t.merge = (t.kchunks == 1 && !t.colsplit && env_mg) ? 1 : 0;
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)k * Cin * CoutW; ++i) mx = std::max(mx, std::fabs(w[i]));
     int e = 0;
@@ -107,9 +110,15 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
                         const float v = (o < Cout) ? w[((size_t)tap * Cin + ci) * CoutW + o] * ws : 0.f;
                         const __half hi = __float2half_rn(v);
                         const __half lo = __float2half_rn(v - __half2float(hi));
-                        const size_t idx = ((size_t)(c / 8) * NC + n) * 8 + (c % 8);
-                        dst[idx] = hi;
-                        dst[(size_t)KC * NC + idx] = lo;
+                        if (t.merge) {   // hi rows then lo rows inside every 8-channel group: B' = [B_hi ; B_lo] (2*NC rows)
+                            const size_t ih = ((size_t)(c / 8) * 2 * NC + n) * 8 + (c % 8);
+                            dst[ih] = hi;
+                            dst[ih + (size_t)NC * 8] = lo;
+                        } else {
+                            const size_t idx = ((size_t)(c / 8) * NC + n) * 8 + (c % 8);
+                            dst[idx] = hi;
+                            dst[(size_t)KC * NC + idx] = lo;
+                        }
                     }
             }
     void* d = nullptr;
@@ -326,7 +335,7 @@ __device__ __forceinline__ void planes_store8(const Planes& pl, long long prow, 
 #define TC_TS(role, idx) do { (void)tr; } while (0)
 #endif
 
-template <int NCT, int CS>
+template <int NCT, int CS, int MG>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
     constexpr int NC = NCT * 16;
     extern __shared__ __align__(128) uint8_t tsm[];
@@ -406,13 +415,22 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         for (int q = 0; q < nq; ++q) {
             const int jl = q / KCH, kc = q - jl * KCH, mb = q & 1;
             const int tile = CS ? jl : 2 * jl + set;
-            const int mi = CS ? mb : set * 2 + mb;       // main accumulator / barrier index
+            const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);       // main accumulator / barrier index
             if (wq == 0) TC_TS(1 + set, q * 5 + 0);
-            mbar_wait(&m_full[mi], (q >> 1) & 1);        // this chunk's MMAs retired: the main accumulator is final
+            mbar_wait(&m_full[mi], MG ? (q & 1) : ((q >> 1) & 1));        // this chunk's MMAs retired: the main accumulator is final
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 1);
-            const uint32_t tmain = tlane + (CS ? (uint32_t)(mb * 2 * NC + ccol) : (uint32_t)(set * 2 + mb) * NC);
-            if (kc == 0) {
+            const uint32_t tmain = tlane + (CS ? (uint32_t)(mb * 2 * NC + ccol) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
+            if (MG) {       // single K-chunk: main = hi*hi, x = hi*lo (second half of the merged N = 2*NC accumulator)
+#pragma unroll
+                for (int cb = 0; cb < NC; cb += 16) {
+                    float v[16], x2[16];
+                    tc_ld16(tmain + cb, v);
+                    tc_ld16(tmain + NC + cb, x2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[cb + j] = v[j] + x2[j];
+                }
+            } else if (kc == 0) {
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += 16) {
                     float v[16];
@@ -438,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             mbar_wait(&c_full[ci], CS ? ((tile >> 1) & 1) : (jl & 1));
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 3);
-            const uint32_t tcorr = tlane + (CS ? (uint32_t)(4 * NC + ci * 2 * NC + ccol) : (uint32_t)(4 + set) * NC);
+            const uint32_t tcorr = tlane + (CS ? (uint32_t)(4 * NC + ci * 2 * NC + ccol) : (MG ? (uint32_t)(set * 3 * NC + 2 * NC) : (uint32_t)(4 + set) * NC));
             const int t0 = (tile_b + tile) * 128;
             const int trow = t0 + wq * 32 + lane;
             const bool rowok = trow < len;
@@ -593,9 +611,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         const bool do_main = warp == 8;
         {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3, M>>4 (M = 128)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(NCW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // merged mode: the hi*hi|hi*lo MMA is N = 2*NC wide over B' = [B_hi ; B_lo]; the lo*hi MMA reads rows 0..NC-1 of B'
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(((MG && do_main) ? 2 * NCW : NCW) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a_s = smem_u32(a_ring), b_s = smem_u32(bst);
-            const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)NCW * 16;
+            const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)(MG ? 2 * NCW : NCW) * 16;
             // descriptors are built once and only their 14-bit start-address field (units of 16 B) is advanced
             // per MMA (no carry: smem < 256 KB)
             const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
@@ -609,18 +628,21 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 const int set = tile & 1, jl = tile >> 1;
                 const int q = CS ? g : jl * KCH + kc;      // position in the accumulator stream (per set when alternating)
                 const int mb = q & 1;
-                const int mi = CS ? mb : set * 2 + mb, ci = CS ? (tile & 1) : set;
+                const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb), ci = CS ? (tile & 1) : set;
                 TC_TS(0, g * 4 + 0);
                 mbar_wait_warp(&a_full[buf], aph);
                 TC_TS(0, g * 4 + 1);
-                if (do_main) { if (q >= 2) mbar_wait_warp(&m_empty[mi], ((q >> 1) - 1) & 1); }                   // main accumulator drained
+                if (do_main) {                                                                                   // main accumulator drained
+                    if (MG) { if (q >= 1) mbar_wait_warp(&m_empty[mi], (q - 1) & 1); }
+                    else if (q >= 2) mbar_wait_warp(&m_empty[mi], ((q >> 1) - 1) & 1);
+                }
                 else if (kc == 0 && (CS ? tile >= 2 : jl >= 1))                                                  // corr accumulator consumed by its epilogue
                     mbar_wait_warp(&c_empty[ci], CS ? (((tile >> 1) - 1) & 1) : ((jl - 1) & 1));
                 tc_fence_after();
                 TC_TS(0, g * 4 + 2);
                 const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
-                const uint32_t tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (uint32_t)(set * 2 + mb) * NC);
-                const uint32_t tcorr = tmem + (CS ? (uint32_t)(4 * NC + ci * 2 * NC) : (uint32_t)(4 + set) * NC);
+                const uint32_t tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
+                const uint32_t tcorr = tmem + (CS ? (uint32_t)(4 * NC + ci * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC + 2 * NC) : (uint32_t)(4 + set) * NC));
                 uint32_t main_acc = 0;                 // the previous partial sum was promoted to registers
                 uint32_t corr_acc = kc == 0 ? 0u : 1u;
                 for (int tap = 0; tap < p.k; ++tap) {
@@ -644,7 +666,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                                 if (do_main) tc_mma_f16(tmain, a, b, idesc, k16 == 0 ? main_acc : 1u);
                                 else {
                                     tc_mma_f16(tcorr, a + a_lo_off, b, idesc, k16 == 0 ? corr_acc : 1u);
-                                    tc_mma_f16(tcorr, a, b + b_lo_off, idesc, 1);
+                                    if (!MG) tc_mma_f16(tcorr, a, b + b_lo_off, idesc, 1);
                                 }
                             }
                         }
@@ -821,20 +843,30 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     if (!tc_make_map(&amap, in, t.xr, w.KC)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<3, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<4, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<4, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     dim3 g((ntiles + tpc - 1) / tpc, nseg, w.nchunks);
-    if (w.colsplit) conv_tc_kernel<4, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap);
+    if (w.colsplit) conv_tc_kernel<4, 1, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap);
+    else if (w.merge) switch (w.NC / 16) {
+        case 1: conv_tc_kernel<1, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 2: conv_tc_kernel<2, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 3: conv_tc_kernel<3, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        default: conv_tc_kernel<4, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+    }
     else switch (w.NC / 16) {
-        case 1: conv_tc_kernel<1, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 2: conv_tc_kernel<2, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 3: conv_tc_kernel<3, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        default: conv_tc_kernel<4, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 1: conv_tc_kernel<1, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 2: conv_tc_kernel<2, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        case 3: conv_tc_kernel<3, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
+        default: conv_tc_kernel<4, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
     }
     if (do_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
         --trace_left;
