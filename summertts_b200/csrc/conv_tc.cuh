@@ -75,7 +75,8 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     // K-chunk: one promotion per chunk
     // 64-channel chunks halve the per-stage barrier traffic of the MMA issuer (measured: 153 -> ~90 cycles per MMA);
     // promotion period = 4*k MMA steps (<= 44), still far inside the accuracy budget (tools/tc_error.py)
-    const int KC = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+    static const int env_kc64 = getenv("STTS_TC_KC64") ? atoi(getenv("STTS_TC_KC64")) : 1;
+    const int KC = (Cin % 64 == 0 && (env_kc64 == 1 || (env_kc64 == 2 && k <= 5))) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
     const int Cr = (Cout + 15) & ~15;
     int NC = Cr;
     t.colsplit = 0;
@@ -90,7 +91,7 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     }
     t.NC = NC; t.nchunks = (Cr + NC - 1) / NC; t.KC = KC; t.kchunks = Cin / KC; t.taps = k;
     static const int env_mg = getenv("STTS_TC_MERGE") ? atoi(getenv("STTS_TC_MERGE")) : 1;
-    t.merge = (t.kchunks == 1 && !t.colsplit && env_mg) ? 1 : 0;
+    t.merge = (t.kchunks == 1 && !t.colsplit && env_mg && k * (KC / 16) <= 24) ? 1 : 0;   // no mid-chunk promotion in merged mode
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)k * Cin * CoutW; ++i) mx = std::max(mx, std::fabs(w[i]));
     int e = 0;
@@ -351,6 +352,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
     const int KC = t.KC, XR = t.xr, KCH = t.kchunks;
     constexpr int NCW = CS ? 2 * NC : NC;     // columns of this CTA (MMA N)
     const int G = NT * KCH;               // global chunks of this CTA
+    // promotion units: the hi*hi accumulator is promoted to fp32 registers every <= 12 MMA steps (UPT taps);
+    // longer runs let the tensor core's truncating accumulator drift (single_speaker_mid: 6.3e-4 -> 8.8e-4)
+    const int UPT = MG ? p.k : max(1, 12 / (KC / 16));   // taps per unit
+    const int U = MG ? 1 : (p.k + UPT - 1) / UPT;        // units per K-chunk
     const int NB = t.nbstages;
     const long long prow_u = planes_row(p.seg, u);   // padded plane row of this utterance's row 0
     long long* tr = (t.trace && blockIdx.x == 0 && blockIdx.y == (gridDim.y >> 1) && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? t.trace : nullptr;
@@ -410,10 +415,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         // alternating mode: set s serves tiles s, s+2, ... with its own main[s][2] / corr[s];
         // column-split mode: both sets serve every tile, set s owns columns [s*NC, (s+1)*NC) of main[2] / corr[2]
         const int ntl = (NT - set + 1) >> 1;
-        const int nq = CS ? G : ntl * KCH;
+        const int nq = (CS ? G : ntl * KCH) * U;
         const int ccol = CS ? set * NC : 0;             // this set's first column inside the CTA's column block
         for (int q = 0; q < nq; ++q) {
-            const int jl = q / KCH, kc = q - jl * KCH, mb = q & 1;
+            const int qc = q / U, unit = q - qc * U;      // K-chunk of the stream, promotion unit inside it
+            const int jl = qc / KCH, kc = qc - jl * KCH, mb = q & 1;
             const int tile = CS ? jl : 2 * jl + set;
             const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);       // main accumulator / barrier index
             if (wq == 0) TC_TS(1 + set, q * 5 + 0);
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
 #pragma unroll
                     for (int j = 0; j < 16; ++j) racc[cb + j] = v[j] + x2[j];
                 }
-            } else if (kc == 0) {
+            } else if (kc == 0 && unit == 0) {
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += 16) {
                     float v[16];
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             tc_fence_before();
             mbar_arrive(&m_empty[mi]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 2);
-            if (kc != KCH - 1) continue;
+            if (kc != KCH - 1 || unit != U - 1) continue;
             // ---------------- epilogue of tile `tile` -------------------------------------------
             const int ci = CS ? (tile & 1) : set;        // corr accumulator / barrier index
             mbar_wait(&c_full[ci], CS ? ((tile >> 1) & 1) : (jl & 1));
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 if (p.epi == EPI_GATE) {
                     float o[8];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) o[j >> 1] = gate_ref(v[j], v[j + 1]);
+                    for (int j = 0; j < 16; j += 2) o[j >> 1] = (t.dbg & 32) ? tanh_ref(v[j]) * sigmoid_ref(v[j + 1]) : gate_ref(v[j], v[j + 1]);
                     const int ob = nb >> 1;
                     if (t.write_f32) {
                         float* d = p.y + row * p.ldy + ob;
@@ -626,26 +632,32 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             int tile = 0, kc = 0;
             for (int g = 0; g < G; ++g) {
                 const int set = tile & 1, jl = tile >> 1;
-                const int q = CS ? g : jl * KCH + kc;      // position in the accumulator stream (per set when alternating)
-                const int mb = q & 1;
-                const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb), ci = CS ? (tile & 1) : set;
+                int q = (CS ? g : jl * KCH + kc) * U;      // position in the accumulator stream (per set when alternating)
+                const int ci = CS ? (tile & 1) : set;
                 TC_TS(0, g * 4 + 0);
                 mbar_wait_warp(&a_full[buf], aph);
                 TC_TS(0, g * 4 + 1);
-                if (do_main) {                                                                                   // main accumulator drained
-                    if (MG) { if (q >= 1) mbar_wait_warp(&m_empty[mi], (q - 1) & 1); }
-                    else if (q >= 2) mbar_wait_warp(&m_empty[mi], ((q >> 1) - 1) & 1);
-                }
-                else if (kc == 0 && (CS ? tile >= 2 : jl >= 1))                                                  // corr accumulator consumed by its epilogue
+                if (!do_main && kc == 0 && (CS ? tile >= 2 : jl >= 1))                                           // corr accumulator consumed by its epilogue
                     mbar_wait_warp(&c_empty[ci], CS ? (((tile >> 1) - 1) & 1) : ((jl - 1) & 1));
                 tc_fence_after();
                 TC_TS(0, g * 4 + 2);
                 const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
-                const uint32_t tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
                 const uint32_t tcorr = tmem + (CS ? (uint32_t)(4 * NC + ci * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC + 2 * NC) : (uint32_t)(4 + set) * NC));
-                uint32_t main_acc = 0;                 // the previous partial sum was promoted to registers
+                uint32_t tmain = 0, main_acc = 0;
+                int mi = 0;
                 uint32_t corr_acc = kc == 0 ? 0u : 1u;
-                for (int tap = 0; tap < p.k; ++tap) {
+                for (int tap = 0, ut = 0; tap < p.k; ++tap) {
+                    if (ut == 0) {   // a promotion unit starts: fresh main accumulator (the previous one was promoted to registers)
+                        const int mb = q & 1;
+                        mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);
+                        tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
+                        main_acc = 0;
+                        if (do_main) {                                                                           // main accumulator drained
+                            if (MG) { if (q >= 1) mbar_wait_warp(&m_empty[mi], (q - 1) & 1); }
+                            else if (q >= 2) mbar_wait_warp(&m_empty[mi], ((q >> 1) - 1) & 1);
+                            tc_fence_after();
+                        }
+                    }
                     int s;
                     if (t.resident) {
                         s = kc * p.k + tap;
@@ -671,15 +683,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                             }
                         }
                         if (!t.resident) tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
+                        if (do_main && (ut == UPT - 1 || tap == p.k - 1)) tc_commit(&m_full[mi]);   // unit complete: publish its partial sum
                     }
                     main_acc = 1;
                     corr_acc = 1;
+                    if (++ut == UPT || tap == p.k - 1) { ut = 0; ++q; }
                 }
                 TC_TS(0, g * 4 + 3);
                 if (elect_one()) {
                     tc_commit(&a_empty[buf]);              // A chunk may be overwritten (needs both issuers)
-                    if (do_main) tc_commit(&m_full[mi]);      // the main accumulator holds this chunk's partial sum
-                    else if (kc == KCH - 1) tc_commit(&c_full[ci]);
+                    if (!do_main && kc == KCH - 1) tc_commit(&c_full[ci]);
                 }
                 __syncwarp();
                 if (++buf == AR) { buf = 0; aph ^= 1; }
