@@ -81,10 +81,13 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     int NC = Cr;
     t.colsplit = 0;
     static const int env_cs = getenv("STTS_TC_COLSPLIT") ? atoi(getenv("STTS_TC_COLSPLIT")) : 1;
+    static const int env_nc32 = getenv("STTS_TC_NC32") ? atoi(getenv("STTS_TC_NC32")) : 0;
     if (Cout >= 128 && KC == 64 && env_cs) {
         // wide layers: N = 128 MMAs (65 cycles each instead of 2 x 53, half the MMA count and A-tile traffic)
         NC = 128;
         t.colsplit = 1;
+    } else if (Cr == 64 && env_nc32) {
+        NC = 32;           // two 32-column chunks: the light (<= 85 register) kernels run two CTAs per SM
     } else if (Cr > 64) {  // split into equal chunks of <= 64 columns (multiple of 16): 64 fp32 register accumulators/thread
         int n = (Cr + 63) / 64;
         NC = (((Cr + n - 1) / n) + 15) & ~15;
@@ -278,19 +281,21 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel (v4: TMA-fed, software-pipelined)
+// the kernel (v5: persistent, TMA-fed, software-pipelined)
 //
-// One CTA = one utterance x `tiles_per_cta` consecutive 128-row time tiles x one N-chunk (NC columns).
-// Work is a stream of "global chunks" g = (tile, K-chunk).  Four agents run concurrently:
-//   TMA lane (warp 6): activation box (hi, lo) of chunk g -> A[g % 2]
-//   producer (warp 5): weight stages through a ring, or loaded ONCE and kept resident when the layer's
-//                      packed weights for this N-chunk fit in shared memory
-//   MMA lane (warp 4): chunk g -> main[g&1] (accumulate = 0 at the chunk's first MMA), corr[tile&1]
-//   warps 0-3 / 4-7  : "set" s = tile & 1 owns TMEM main[s][2] + corr[s]: promotes each chunk's partial sum
-//                      into fp32 registers and runs the tile's epilogue, while the other set already
-//                      serves the next tile
-// so loads, MMAs, promotion and the epilogue of the previous tile all overlap
-// (TMEM: main[2][2] + corr[2] = 6*NC columns; one CTA per SM).
+// One CTA per SM walks a stream of work tiles = (utterance, 128-row time tile, column chunk of NC / 2*NC outputs),
+// round-robin over the flat grid (TileIt).  Inside the CTA the work is a stream of "global chunks" g = (tile, K-chunk)
+// served by concurrent agents:
+//   warp 10 (one lane)  : activation TMA boxes (hi, lo) of chunk g -> A ring
+//   warp 9  (one lane)  : weight stages through a cp.async.bulk ring, or loaded ONCE and kept resident when the
+//                         layer's packed weights for this column chunk fit in shared memory
+//   warp 8 / warp 11    : MMA issuers: hi*hi into main[..], the lo*hi / hi*lo corrections into corr[..]
+//   warps 0-3 / 4-7     : two promotion/epilogue "sets".  Alternating mode: set s = tile & 1 owns TMEM main[s][2] +
+//                         corr[s]; column-split mode (CS): both sets serve every tile, 64 columns each of an N = 128
+//                         accumulator.  A set promotes each unit's hi*hi partial sum into fp32 registers and runs the
+//                         tile's epilogue while the MMA warps already work on the next tile.
+// so loads, MMAs, promotion and the epilogue of the previous tile all overlap; TMEM allocation, barrier setup and
+// resident weights are paid once per SM and there is no wave quantisation.
 // ---------------------------------------------------------------------------------------------
 struct TcP {
     const __half* wp;
@@ -298,7 +303,8 @@ struct TcP {
     float inv_scale;
     int tmem_cols;      // power of two >= 6*NC
     int xr;             // A tile rows incl. halo (TMA box rows)
-    int tiles_per_cta;
+    int gx;             // 128-row tiles of the longest utterance
+    int work_items;     // gx * utterances * nchunks (flat work grid walked by the persistent CTAs)
     int resident;       // 1: all kchunks*taps weight stages stay in smem for the CTA's lifetime
     int nbstages;       // weight ring depth, or kchunks*taps when resident
     int aring;          // activation ring depth (2..4)
@@ -336,29 +342,45 @@ __device__ __forceinline__ void planes_store8(const Planes& pl, long long prow, 
 #define TC_TS(role, idx) do { (void)tr; } while (0)
 #endif
 
+// CTA-local walk over this CTA's share of the (utterance, 128-row tile, column chunk) grid.  The kernel is persistent:
+// CTA c serves flat work indices c, c + gridDim.x, ... (index = (u * gx + x) * nchunks + z, gridDim.x a multiple of
+// nchunks so z is fixed per CTA); every role walks the same sequence, tiles past an utterance's end are skipped.
+struct TileIt {
+    int w, W, step, gx, nchunks;
+    int u, x, z, seg0, len;
+    long long prow_u;
+};
+__device__ __forceinline__ bool tile_next(TileIt& it, const Seg& seg) {
+    while (it.w < it.W) {
+        const int w = it.w;
+        it.w += it.step;
+        const int r = w / it.nchunks, z = w - r * it.nchunks;
+        const int u = r / it.gx, x = r - u * it.gx;
+        const int len = seg_len(seg, u);
+        if (x * 128 >= len) continue;
+        it.u = u; it.x = x; it.z = z; it.len = len;
+        it.seg0 = seg_start(seg, u);
+        it.prow_u = planes_row(seg, u);       // padded plane row of this utterance's row 0
+        return true;
+    }
+    return false;
+}
+
 template <int NCT, int CS, int MG>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
+__global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
     constexpr int NC = NCT * 16;
     extern __shared__ __align__(128) uint8_t tsm[];
-    const int u = blockIdx.y;
-    const int seg0 = seg_start(p.seg, u);
-    const int len = seg_len(p.seg, u);
-    const int ntiles_u = (len + 127) >> 7;
-    const int tile_b = blockIdx.x * t.tiles_per_cta;
-    if (tile_b >= ntiles_u) return;
-    const int NT = min(t.tiles_per_cta, ntiles_u - tile_b);
-    const int nchunk = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = t.KC, XR = t.xr, KCH = t.kchunks;
     constexpr int NCW = CS ? 2 * NC : NC;     // columns of this CTA (MMA N)
-    const int G = NT * KCH;               // global chunks of this CTA
     // promotion units: the hi*hi accumulator is promoted to fp32 registers every <= 12 MMA steps (UPT taps);
     // longer runs let the tensor core's truncating accumulator drift (single_speaker_mid: 6.3e-4 -> 8.8e-4)
     const int UPT = MG ? p.k : max(1, 12 / (KC / 16));   // taps per unit
     const int U = MG ? 1 : (p.k + UPT - 1) / UPT;        // units per K-chunk
     const int NB = t.nbstages;
-    const long long prow_u = planes_row(p.seg, u);   // padded plane row of this utterance's row 0
-    long long* tr = (t.trace && blockIdx.x == 0 && blockIdx.y == (gridDim.y >> 1) && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? t.trace : nullptr;
+    TileIt it;
+    it.w = blockIdx.x; it.W = t.work_items; it.step = gridDim.x; it.gx = t.gx; it.nchunks = t.nchunks;
+    long long* tr = (t.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? t.trace : nullptr;
 
     // ---- shared memory carve-up -------------------------------------------------------------
     const uint32_t a_plane = (((uint32_t)(KC / 8) * XR * 16) + 127u) & ~127u;   // bytes per A plane (128B aligned)
@@ -378,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
     uint64_t* b_empty = bars + 20;    // [TC_MAX_RING]
     uint64_t* b_full = bars + 20 + TC_MAX_RING;   // [NB]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + NB);
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [NC] bias (+ speaker vector) of this CTA's columns
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [set][2][NC] bias (+ speaker vector), double-buffered per tile
 
     if (tid == 0) {
         for (int i = 0; i < TC_MAX_ARING; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }   // both MMA warps release
@@ -392,15 +414,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(t.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < NCW) {
-        const int n = nchunk * NCW + tid;
-        float b = 0.f;
-        if (n < p.Cout) {
-            if (p.bias) b = __ldg(p.bias + n);
-            if (p.gvec) b += __ldg(p.gvec + (size_t)u * p.ldg + n);
-        }
-        sbias[tid] = b;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -412,15 +425,32 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
         const float isc = t.inv_scale;
         float racc[NC];
-        // alternating mode: set s serves tiles s, s+2, ... with its own main[s][2] / corr[s];
+        // alternating mode: set s serves the CTA's tiles s, s+2, ... with its own main[s][2] / corr[s];
         // column-split mode: both sets serve every tile, set s owns columns [s*NC, (s+1)*NC) of main[2] / corr[2]
-        const int ntl = (NT - set + 1) >> 1;
-        const int nq = (CS ? G : ntl * KCH) * U;
         const int ccol = CS ? set * NC : 0;             // this set's first column inside the CTA's column block
-        for (int q = 0; q < nq; ++q) {
-            const int qc = q / U, unit = q - qc * U;      // K-chunk of the stream, promotion unit inside it
-            const int jl = qc / KCH, kc = qc - jl * KCH, mb = q & 1;
-            const int tile = CS ? jl : 2 * jl + set;
+        const int tset = tid & 127;                     // thread index inside the set
+        int q = 0;                                      // position in this set's accumulator stream
+        int jl = 0;                                     // tiles this set has served
+        for (int tile = 0; tile_next(it, p.seg); ++tile) {
+          if (!CS && (tile & 1) != set) continue;
+          const int u = it.u, seg0 = it.seg0, len = it.len;
+          const long long prow_u = it.prow_u;
+          const int nchunk = it.z;
+          const int ntiles_u = (len + 127) >> 7;
+          float* sb = sbias + (set * 2 + (jl & 1)) * NC;
+          if (tset < NC) {        // bias (+ speaker vector) of this tile's columns; published by the set's named barrier
+              const int n = nchunk * NCW + ccol + tset;
+              float bv = 0.f;
+              if (n < p.Cout) {
+                  if (p.bias) bv = __ldg(p.bias + n);
+                  if (p.gvec) bv += __ldg(p.gvec + (size_t)u * p.ldg + n);
+              }
+              sb[tset] = bv;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+          for (int kc = 0; kc < KCH; ++kc)
+          for (int unit = 0; unit < U; ++unit, ++q) {
+            const int mb = q & 1;
             const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);       // main accumulator / barrier index
             if (wq == 0) TC_TS(1 + set, q * 5 + 0);
             mbar_wait(&m_full[mi], MG ? (q & 1) : ((q >> 1) & 1));        // this chunk's MMAs retired: the main accumulator is final
@@ -463,7 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 3);
             const uint32_t tcorr = tlane + (CS ? (uint32_t)(4 * NC + ci * 2 * NC + ccol) : (MG ? (uint32_t)(set * 3 * NC + 2 * NC) : (uint32_t)(4 + set) * NC));
-            const int t0 = (tile_b + tile) * 128;
+            const int t0 = it.x * 128;
             const int trow = t0 + wq * 32 + lane;
             const bool rowok = trow < len;
             const size_t row = (size_t)(seg0 + (rowok ? trow : 0));
@@ -477,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 if (!rowok || (t.dbg & 2)) continue;
                 const int nb = nchunk * NCW + ccol + cb;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], isc, sbias[ccol + cb + j]);
+                for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], isc, sb[cb + j]);
                 if (p.epi == EPI_GATE) {
                     float o[8];
 #pragma unroll
@@ -576,7 +606,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             }
             // zero the gap rows adjoining this utterance in the output planes (first / last tile only)
             if (t.yp.base || t.y2p.base) {
-                const bool first = (tile_b + tile) == 0, last = (tile_b + tile) == ntiles_u - 1;
+                const bool first = it.x == 0, last = it.x == ntiles_u - 1;
                 if (first || last) {
                     const int tidl = wq * 32 + lane;
                     for (int which = 0; which < 2; ++which) {
@@ -608,6 +638,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             tc_fence_before();
             mbar_arrive(&c_empty[ci]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 4);
+          }
+          ++jl;
         }
     } else if (warp == 8 || warp == 11) {
         // ================= MMA issuers (warp-uniform loops, one elected lane issues) ============
@@ -629,8 +661,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
             const int nk16 = KC / 16;
             int bs = 0; uint32_t bph = 0;      // weight ring slot / phase
             int buf = 0; uint32_t aph = 0;     // activation ring slot / phase
-            int tile = 0, kc = 0;
-            for (int g = 0; g < G; ++g) {
+            int g = 0;                         // running (tile, K-chunk) counter of this CTA
+            for (int tile = 0; tile_next(it, p.seg); ++tile)
+            for (int kc = 0; kc < KCH; ++kc, ++g) {
                 const int set = tile & 1, jl = tile >> 1;
                 int q = (CS ? g : jl * KCH + kc) * U;      // position in the accumulator stream (per set when alternating)
                 const int ci = CS ? (tile & 1) : set;
@@ -696,29 +729,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
                 }
                 __syncwarp();
                 if (++buf == AR) { buf = 0; aph ^= 1; }
-                if (++kc == KCH) { kc = 0; ++tile; }
             }
         }
     } else if (warp == 9) {
         // ================= weight producer (bulk-copy engine) ==================================
         if (lane == 0) {
             const int per_tile = KCH * p.k;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(t.wp) + (size_t)nchunk * per_tile * b_stage;
-            if (t.resident) {
+            TileIt probe = it;
+            if (t.resident && tile_next(probe, p.seg)) {      // the column chunk is fixed per CTA (gridDim.x is a multiple of nchunks)
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(t.wp) + (size_t)(blockIdx.x % t.nchunks) * per_tile * b_stage;
                 for (int s = 0; s < per_tile; ++s) {
                     mbar_expect_tx(&b_full[s], b_stage);
                     bulk_g2s(bst + (size_t)s * b_stage, src + (size_t)s * b_stage, b_stage, &b_full[s]);
                 }
-            } else {
-                const int nsteps = NT * per_tile;
-                int s = 0, off = 0; uint32_t ph = 1;   // first pass over the ring needs no wait
-                for (int step = 0; step < nsteps; ++step) {
-                    if (step >= NB) mbar_wait(&b_empty[s], ph);
-                    TC_TS(4, step);
-                    mbar_expect_tx(&b_full[s], b_stage);
-                    bulk_g2s(bst + (size_t)s * b_stage, src + (size_t)off * b_stage, b_stage, &b_full[s]);
-                    if (++s == NB) { s = 0; ph ^= 1; }
-                    if (++off == per_tile) off = 0;
+            } else if (!t.resident) {
+                int s = 0, step = 0; uint32_t ph = 1;   // first pass over the ring needs no wait
+                while (tile_next(it, p.seg)) {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(t.wp) + (size_t)it.z * per_tile * b_stage;
+                    for (int off = 0; off < per_tile; ++off, ++step) {
+                        if (step >= NB) mbar_wait(&b_empty[s], ph);
+                        TC_TS(4, step);
+                        mbar_expect_tx(&b_full[s], b_stage);
+                        bulk_g2s(bst + (size_t)s * b_stage, src + (size_t)off * b_stage, b_stage, &b_full[s]);
+                        if (++s == NB) { s = 0; ph ^= 1; }
+                    }
                 }
             }
         }
@@ -727,18 +761,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvP p, cons
         // ================= activation producer (TMA) ===========================================
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)(KC / 8) * XR * 16;
-            int buf = 0, tile = 0, kc = 0; uint32_t ph = 1;
-            for (int g = 0; g < G; ++g) {
-                if (g >= AR) mbar_wait(&a_empty[buf], ph);   // MMAs of chunk g-AR retired
-                const long long r0 = prow_u + (long long)(tile_b + tile) * 128 - p.padl;   // >= 0: TC_GAP >= padl
-                uint8_t* dst = a_ring + (size_t)buf * a_buf;
-                if ((t.dbg & 1) && g >= AR) { mbar_arrive(&a_full[buf]); if (++buf == AR) { buf = 0; ph ^= 1; } if (++kc == KCH) { kc = 0; ++tile; } continue; }
-                TC_TS(3, g);
-                mbar_expect_tx(&a_full[buf], 2 * box_bytes);
-                tma_load_3d(dst, &amap, 0, (int)r0, kc * (KC / 8), &a_full[buf]);
-                tma_load_3d(dst + a_plane, &amap, 0, (int)r0, t.in_groups + kc * (KC / 8), &a_full[buf]);
-                if (++buf == AR) { buf = 0; ph ^= 1; }
-                if (++kc == KCH) { kc = 0; ++tile; }
+            int buf = 0, g = 0; uint32_t ph = 1;
+            while (tile_next(it, p.seg)) {
+                const long long r0 = it.prow_u + (long long)it.x * 128 - p.padl;   // >= 0: TC_GAP >= padl
+                for (int kc = 0; kc < KCH; ++kc, ++g) {
+                    if (g >= AR) mbar_wait(&a_empty[buf], ph);   // MMAs of chunk g-AR retired
+                    uint8_t* dst = a_ring + (size_t)buf * a_buf;
+                    if ((t.dbg & 1) && g >= AR) { mbar_arrive(&a_full[buf]); if (++buf == AR) { buf = 0; ph ^= 1; } continue; }
+                    TC_TS(3, g);
+                    mbar_expect_tx(&a_full[buf], 2 * box_bytes);
+                    tma_load_3d(dst, &amap, 0, (int)r0, kc * (KC / 8), &a_full[buf]);
+                    tma_load_3d(dst + a_plane, &amap, 0, (int)r0, t.in_groups + kc * (KC / 8), &a_full[buf]);
+                    if (++buf == AR) { buf = 0; ph ^= 1; }
+                }
             }
         }
         __syncwarp();
@@ -757,15 +792,16 @@ struct TcPlan {
     size_t smem;
     int resident, nbstages, aring;
 };
-inline TcPlan tc_plan(const TcWeights& w, int k, int dil, bool want_resident) {
+inline TcPlan tc_plan(const TcWeights& w, int k, int dil, bool want_resident, size_t budget = 190 * 1024) {
     TcPlan pl;
     const int xr = 128 + (k - 1) * dil;
     const size_t a_plane = (((size_t)(w.KC / 8) * xr * 16) + 127) & ~size_t(127);
     const size_t a_buf = 2 * a_plane;   // hi | lo
     const size_t stage = (size_t)2 * w.KC * w.NC * 2;
     const int per_tile = w.kchunks * k;
-    const size_t budget = 190 * 1024;   // one CTA per SM: use the shared memory for deep rings (latency hiding)
-    const size_t misc = (20 + TC_MAX_RING + TC_MAX_BSTAGES) * 8 + 16 + 128 * 4 + 128;
+    // default budget: one CTA per SM, deep rings hide latency; the light (NC <= 32) kernels are planned with ~110 KB
+    // so that two CTAs share an SM (twice the epilogue warps in flight)
+    const size_t misc = (20 + TC_MAX_RING + TC_MAX_BSTAGES) * 8 + 16 + 256 * 4 + 128;
     pl.aring = ((size_t)3 * a_buf + 4 * stage + misc <= budget) ? 3 : 2;
     const size_t a = (size_t)pl.aring * a_buf;
     pl.resident = (want_resident && per_tile <= TC_MAX_BSTAGES && a + stage * per_tile + misc <= budget) ? 1 : 0;
@@ -831,15 +867,52 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     t.in_groups = in.C / 8;
     t.yp = out.yp; t.y2p = out.y2p; t.out_act = out.out_act; t.out_slope = out.out_slope; t.write_f32 = out.write_f32 ? 1 : 0;
     const int ntiles = (maxlen + 127) / 128;
-    // several tiles per CTA amortise TMEM allocation / barrier setup and let the epilogue of one tile hide
-    // behind the MMAs of the next; keep a grid of >= ~8 CTAs per SM when the problem allows it
-    // (one CTA per SM: 352 threads x 128 registers) -> the two epilogue sets alternate tiles inside the CTA
-    int tpc = std::min(ntiles, 8);
-    const long per_tile_ctas = (long)nseg * w.nchunks;
-    while (tpc > 2 && per_tile_ctas * ((ntiles + tpc - 1) / tpc) < 148L * 2) --tpc;
-    static const int env_tpc = getenv("STTS_TC_TPC") ? atoi(getenv("STTS_TC_TPC")) : 0;   // tuning knob
-    if (env_tpc > 0) tpc = std::min(env_tpc, std::max(1, ntiles));
-    t.tiles_per_cta = tpc;
+    // persistent CTAs, one per SM, walk the flat (utterance, tile, column chunk) grid round-robin: no wave quantisation,
+    // TMEM allocation / barrier setup / resident weights paid once per SM.  The CTA count is a multiple of nchunks so
+    // every CTA keeps one column chunk (resident weights stay valid for its whole life).
+    static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+    const long long W = (long long)ntiles * nseg * w.nchunks;
+    if (W <= 0 || W > 0x7fffffffLL) return -1;
+    typedef void (*Kern)(const ConvP, const TcP, const CUtensorMap);
+    static const Kern kerns[9] = {conv_tc_kernel<1, 0, 0>, conv_tc_kernel<2, 0, 0>, conv_tc_kernel<3, 0, 0>, conv_tc_kernel<4, 0, 0>,
+                                  conv_tc_kernel<1, 0, 1>, conv_tc_kernel<2, 0, 1>, conv_tc_kernel<3, 0, 1>, conv_tc_kernel<4, 0, 1>,
+                                  conv_tc_kernel<4, 1, 0>};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 9; ++i) cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int nct = std::min(4, w.NC / 16);
+    const int ki = w.colsplit ? 8 : (w.merge ? 4 : 0) + nct - 1;
+    const Kern kern = kerns[ki];
+    // CTAs per SM: registers / shared memory (occupancy query) and TMEM columns (a CTA that could not allocate would
+    // block until a co-resident persistent CTA has finished its whole stream)
+    int per_sm = 1;
+    size_t budget = 190 * 1024;
+    {
+        if (nct <= 2 && !w.colsplit) {
+            const TcPlan small = tc_plan(w, p.k, p.dil, true, 110 * 1024);
+            if (small.smem <= 112 * 1024) budget = 110 * 1024;
+        }
+        const TcPlan pl0 = tc_plan(w, p.k, p.dil, true, budget);
+        static int regs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (!regs[ki]) {
+            cudaFuncAttributes fa;
+            regs[ki] = (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 255;
+        }
+        const int warp_regs = ((regs[ki] * 32 + 511) / 512) * 512;             // register allocation unit: 512 per warp
+        const int by_regs = 65536 / (warp_regs * (TC_THREADS / 32));
+        const int by_smem = (int)((size_t)(227 * 1024) / (pl0.smem + 1024));
+        per_sm = std::max(1, std::min(std::min(by_regs, by_smem), 512 / cols));
+    }
+    static const int env_grid = getenv("STTS_TC_GRID") ? atoi(getenv("STTS_TC_GRID")) : 0;     // tuning knobs
+    static const int env_psm = getenv("STTS_TC_PERSM") ? atoi(getenv("STTS_TC_PERSM")) : 0;
+    if (env_psm > 0) per_sm = std::min(per_sm, env_psm);
+    int ctas = env_grid > 0 ? env_grid : sms * per_sm;
+    if (w.nchunks <= ctas) ctas -= ctas % w.nchunks;
+    if ((long long)ctas > W) ctas = (int)W;
+    t.gx = ntiles; t.work_items = (int)W;
+    const bool zfixed = ctas % w.nchunks == 0;
     static const int env_dbg = getenv("STTS_TC_DBG") ? atoi(getenv("STTS_TC_DBG")) : 0;
     t.dbg = env_dbg;
     static long long* trace_buf = nullptr;
@@ -849,38 +922,19 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     if (do_trace && !trace_buf) { cudaMalloc(&trace_buf, 5 * 1024 * 8); }
     if (do_trace) cudaMemsetAsync(trace_buf, 0, 5 * 1024 * 8, stream);
     t.trace = do_trace ? trace_buf : nullptr;
-    const TcPlan pl = tc_plan(w, p.k, p.dil, tpc >= 2);
+    const TcPlan pl = tc_plan(w, p.k, p.dil, zfixed && W >= 2LL * ctas, budget);
     t.resident = pl.resident; t.nbstages = pl.nbstages; t.aring = pl.aring;
     t.colsplit = w.colsplit;
     alignas(64) CUtensorMap amap;
     if (!tc_make_map(&amap, in, t.xr, w.KC)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<3, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<3, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<4, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+    dim3 g(ctas, 1, 1);
+    static const int env_verbose = getenv("STTS_TC_VERBOSE") ? atoi(getenv("STTS_TC_VERBOSE")) : 0;
+    if (env_verbose > 0) {
+        static int left = env_verbose;
+        if (left > 0) { --left; fprintf(stderr, "tc_conv: Cin=%d Cout=%d k=%d dil=%d NC=%d KC=%d cs=%d mg=%d items=%d ctas=%d per_sm=%d smem=%zu resident=%d nb=%d ar=%d tmem=%d\n",
+                                        p.Cin, p.Cout, p.k, p.dil, w.NC, w.KC, w.colsplit, w.merge, t.work_items, ctas, per_sm, pl.smem, pl.resident, pl.nbstages, pl.aring, cols); }
     }
-    dim3 g((ntiles + tpc - 1) / tpc, nseg, w.nchunks);
-    if (w.colsplit) conv_tc_kernel<4, 1, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap);
-    else if (w.merge) switch (w.NC / 16) {
-        case 1: conv_tc_kernel<1, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 2: conv_tc_kernel<2, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 3: conv_tc_kernel<3, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        default: conv_tc_kernel<4, 0, 1><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-    }
-    else switch (w.NC / 16) {
-        case 1: conv_tc_kernel<1, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 2: conv_tc_kernel<2, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        case 3: conv_tc_kernel<3, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-        default: conv_tc_kernel<4, 0, 0><<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap); break;
-    }
+    kern<<<g, TC_THREADS, pl.smem, stream>>>(p, t, amap);
     if (do_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
         --trace_left;
         std::vector<long long> h(5 * 1024);
@@ -889,7 +943,7 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
         long long t0 = 0;
         for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
         static const char* names[5] = {"mma", "set0", "set1", "aprod", "bprod"};
-        fprintf(stderr, "TRACE grid=(%d,%d,%d) tpc=%d KCH=%d k=%d NC=%d KC=%d resident=%d nb=%d ar=%d\n", g.x, g.y, g.z, tpc, w.kchunks, p.k, w.NC, w.KC, pl.resident, pl.nbstages, pl.aring);
+        fprintf(stderr, "TRACE grid=(%d,%d,%d) items=%d KCH=%d k=%d NC=%d KC=%d resident=%d nb=%d ar=%d\n", g.x, g.y, g.z, t.work_items, w.kchunks, p.k, w.NC, w.KC, pl.resident, pl.nbstages, pl.aring);
         for (int r = 0; r < 5; ++r) {
             fprintf(stderr, " %s:", names[r]);
             for (int i = 0; i < 1024; ++i) if (h[r * 1024 + i]) fprintf(stderr, " %d:%lld", i, h[r * 1024 + i] - t0);
