@@ -377,6 +377,9 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
     // longer runs let the tensor core's truncating accumulator drift (single_speaker_mid: 6.3e-4 -> 8.8e-4)
     const int UPT = MG ? p.k : max(1, 12 / (KC / 16));   // taps per unit
     const int U = MG ? 1 : (p.k + UPT - 1) / UPT;        // units per K-chunk
+    // short chunks (1x1 convs): one unit spans CPU consecutive K-chunks (still <= 12 MMA steps) -> fewer promotions
+    const int CPU = (!MG && U == 1) ? max(1, 12 / (p.k * (KC / 16))) : 1;
+    const int NU = U > 1 ? KCH * U : (KCH + CPU - 1) / CPU;   // promotion units per tile
     const int NB = t.nbstages;
     TileIt it;
     it.w = blockIdx.x; it.W = t.work_items; it.step = gridDim.x; it.gx = t.gx; it.nchunks = t.nchunks;
@@ -448,8 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
               sb[tset] = bv;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
-          for (int kc = 0; kc < KCH; ++kc)
-          for (int unit = 0; unit < U; ++unit, ++q) {
+          for (int un = 0; un < NU; ++un, ++q) {
             const int mb = q & 1;
             const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);       // main accumulator / barrier index
             if (wq == 0) TC_TS(1 + set, q * 5 + 0);
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
 #pragma unroll
                     for (int j = 0; j < 16; ++j) racc[cb + j] = v[j] + x2[j];
                 }
-            } else if (kc == 0 && unit == 0) {
+            } else if (un == 0) {
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += 16) {
                     float v[16];
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
             tc_fence_before();
             mbar_arrive(&m_empty[mi]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 2);
-            if (kc != KCH - 1 || unit != U - 1) continue;
+            if (un != NU - 1) continue;
             // ---------------- epilogue of tile `tile` -------------------------------------------
             const int ci = CS ? (tile & 1) : set;        // corr accumulator / barrier index
             mbar_wait(&c_full[ci], CS ? ((tile >> 1) & 1) : (jl & 1));
@@ -662,10 +664,15 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
             int bs = 0; uint32_t bph = 0;      // weight ring slot / phase
             int buf = 0; uint32_t aph = 0;     // activation ring slot / phase
             int g = 0;                         // running (tile, K-chunk) counter of this CTA
+            int qs[2] = {0, 0};                // position in the accumulator stream (per set when alternating)
+            uint32_t tmain = 0, main_acc = 0;
+            int mi = 0;
             for (int tile = 0; tile_next(it, p.seg); ++tile)
             for (int kc = 0; kc < KCH; ++kc, ++g) {
                 const int set = tile & 1, jl = tile >> 1;
-                int q = (CS ? g : jl * KCH + kc) * U;      // position in the accumulator stream (per set when alternating)
+                int& q = qs[CS ? 0 : set];
+                const bool u_first = U > 1 || kc % CPU == 0;                          // a unit may start / end in this chunk
+                const bool u_last = U > 1 || kc % CPU == CPU - 1 || kc == KCH - 1;
                 const int ci = CS ? (tile & 1) : set;
                 TC_TS(0, g * 4 + 0);
                 mbar_wait_warp(&a_full[buf], aph);
@@ -676,11 +683,9 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                 TC_TS(0, g * 4 + 2);
                 const uint64_t dA0 = a_bits | (uint64_t)(((a_s + (uint32_t)buf * a_buf) & 0x3FFFFu) >> 4);
                 const uint32_t tcorr = tmem + (CS ? (uint32_t)(4 * NC + ci * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC + 2 * NC) : (uint32_t)(4 + set) * NC));
-                uint32_t tmain = 0, main_acc = 0;
-                int mi = 0;
                 uint32_t corr_acc = kc == 0 ? 0u : 1u;
                 for (int tap = 0, ut = 0; tap < p.k; ++tap) {
-                    if (ut == 0) {   // a promotion unit starts: fresh main accumulator (the previous one was promoted to registers)
+                    if (ut == 0 && (u_first || tap > 0)) {   // a promotion unit starts: fresh main accumulator (the previous one was promoted to registers)
                         const int mb = q & 1;
                         mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);
                         tmain = tmem + (CS ? (uint32_t)(mb * 2 * NC) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
@@ -716,11 +721,14 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                             }
                         }
                         if (!t.resident) tc_commit(&b_empty[s]);      // frees this weight stage when the MMAs above retire
-                        if (do_main && (ut == UPT - 1 || tap == p.k - 1)) tc_commit(&m_full[mi]);   // unit complete: publish its partial sum
+                        if (do_main && (U > 1 ? (ut == UPT - 1 || tap == p.k - 1) : (tap == p.k - 1 && u_last)))
+                            tc_commit(&m_full[mi]);   // unit complete: publish its partial sum
                     }
                     main_acc = 1;
                     corr_acc = 1;
-                    if (++ut == UPT || tap == p.k - 1) { ut = 0; ++q; }
+                    ++ut;
+                    if (U > 1 ? (ut == UPT || tap == p.k - 1) : (tap == p.k - 1 && u_last)) ++q;
+                    if (ut == UPT || tap == p.k - 1) ut = 0;
                 }
                 TC_TS(0, g * 4 + 3);
                 if (elect_one()) {

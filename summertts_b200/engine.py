@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstts_b200.so")
+LIB_PATH = os.environ.get("STTS_B200_LIB") or os.path.join(_HERE, "libstts_b200.so")   # override: instrumented dev builds
 
 # every symbol include/stts_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
