@@ -314,6 +314,13 @@ struct TcP {
     Planes yp, y2p;
     int out_act; float out_slope;
     int write_f32;      // 0: planes only (p.y may be null)
+    // "tile-transposed" fp32 tensors (dense, ld == C): inside each 128-row tile of an utterance the block is stored
+    // column-major, elem(r, c) = base + (seg0 + t0) * C + c * tr + r  (tr = rows of the tile).  With one thread per
+    // row every epilogue access is a coalesced 128-byte warp transaction instead of 32 scattered 16-byte ones
+    // (measured: the row-major read-modify-write made res_skip 28k cycles per tile).  Only tensors whose every
+    // reader and writer is a tensor-core epilogue use it (WN h / skip, ResBlock1 x, MRF accumulator).
+    int y_tt, y2_tt, res_tt, acc_tt;
+    const float* acc_src;   // EPI_ACCUM / EPI_ACCUM_DIV: accumulate onto this tensor instead of y (null: y itself)
     long long* trace;   // optional clock64 trace of one CTA (tools/tc_trace.py): [5 roles][1024]
     int dbg;            // timing experiments (STTS_TC_DBG): 1 = skip activation TMA after warm-up, 2 = skip epilogue stores
 };
@@ -334,6 +341,47 @@ __device__ __forceinline__ void planes_store8(const Planes& pl, long long prow, 
     const size_t o = ((size_t)(ch0 >> 3) * pl.rows_p + (size_t)prow) * 8;
     *reinterpret_cast<uint4*>(pl.base + o) = hi;
     *reinterpret_cast<uint4*>(pl.base + (size_t)(pl.C >> 3) * pl.rows_p * 8 + o) = lo;
+}
+
+// 16 consecutive columns [c0, c0+16) of one row of an fp32 tensor: row-major (vectorised when aligned) or
+// tile-transposed (tt: column stride = tr rows, coalesced across the warp's 32 rows).  nv = valid columns (<= 16).
+__device__ __forceinline__ void load16(const float* base, int ld, bool tt, size_t row, size_t tbase, int tr, int rl,
+                                       int c0, int nv, float* o) {
+    if (tt) {
+        const float* q = base + tbase * ld + (size_t)c0 * tr + rl;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = (j < nv) ? __ldcg(q + (size_t)j * tr) : 0.f;
+    } else {
+        const float* q = base + row * ld + c0;
+        if (nv == 16 && ((((uintptr_t)q) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 f = __ldcg(reinterpret_cast<const float4*>(q) + j);
+                o[4 * j] = f.x; o[4 * j + 1] = f.y; o[4 * j + 2] = f.z; o[4 * j + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = (j < nv) ? __ldcg(q + j) : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void store16(float* base, int ld, bool tt, size_t row, size_t tbase, int tr, int rl,
+                                        int c0, int nv, const float* v) {
+    if (tt) {
+        float* q = base + tbase * ld + (size_t)c0 * tr + rl;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j < nv) __stcg(q + (size_t)j * tr, v[j]);
+    } else {
+        float* q = base + row * ld + c0;
+        if (nv == 16 && ((((uintptr_t)q) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                __stcg(reinterpret_cast<float4*>(q) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < nv) q[j] = v[j];
+        }
+    }
 }
 
 #ifdef STTS_TC_TRACE_BUILD   // tools/tc_trace.py builds with this; production kernels carry no clock reads
@@ -366,7 +414,10 @@ __device__ __forceinline__ bool tile_next(TileIt& it, const Seg& seg) {
     return false;
 }
 
-template <int NCT, int CS, int MG>
+// SU = 1 (host: the whole tile is a single promotion unit, e.g. 1x1 convs with Cin <= 192): no register promotion at
+// all -- the epilogue reads main + corr straight from TMEM, and the 64 registers this frees hold the old values of a
+// read-modify-write epilogue (res_skip), loaded at tile start so their latency hides behind the tile's MMAs.
+template <int NCT, int CS, int MG, int SU = 0>
 __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel(const ConvP p, const TcP t, const __grid_constant__ CUtensorMap amap) {
     constexpr int NC = NCT * 16;
     extern __shared__ __align__(128) uint8_t tsm[];
@@ -451,6 +502,24 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
               sb[tset] = bv;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+          float old[SU ? NC : 1];
+          if (SU && p.epi == EPI_RESSKIP) {       // old h / skip values of this thread's row: in flight during the MMAs
+              const int t0p = it.x * 128, trp = min(128, len - t0p), rlp = wq * 32 + lane;
+              const bool okp = t0p + rlp < len;
+              const size_t rowp = (size_t)(seg0 + (okp ? t0p + rlp : 0)), tbp = (size_t)(seg0 + t0p);
+#pragma unroll
+              for (int cb = 0; cb < (SU ? NC : 0); cb += 16) {
+                  const int nb = nchunk * NCW + ccol + cb;
+                  const bool toX = nb < p.split;
+                  const int oc = toX ? nb : nb - p.split;
+                  if (okp && nb < p.Cout && (toX || !p.y2_store))
+                      load16(toX ? p.y : p.y2, toX ? p.ldy : p.ldy2, toX ? t.y_tt : t.y2_tt, rowp, tbp, trp, rlp, oc, min(16, p.Cout - nb), old + cb);
+                  else {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) old[cb + j] = 0.f;
+                  }
+              }
+          }
           for (int un = 0; un < NU; ++un, ++q) {
             const int mb = q & 1;
             const int mi = CS ? mb : (MG ? set * 2 : set * 2 + mb);       // main accumulator / barrier index
@@ -459,7 +528,8 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
             tc_fence_after();
             if (wq == 0) TC_TS(1 + set, q * 5 + 1);
             const uint32_t tmain = tlane + (CS ? (uint32_t)(mb * 2 * NC + ccol) : (MG ? (uint32_t)(set * 3 * NC) : (uint32_t)(set * 2 + mb) * NC));
-            if (MG) {       // single K-chunk: main = hi*hi, x = hi*lo (second half of the merged N = 2*NC accumulator)
+            if (SU) {       // single unit: the epilogue reads the main accumulator straight from TMEM
+            } else if (MG) {       // single K-chunk: main = hi*hi, x = hi*lo (second half of the merged N = 2*NC accumulator)
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += 16) {
                     float v[16], x2[16];
@@ -485,8 +555,10 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                     for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&m_empty[mi]);
+            if (!SU) {
+                tc_fence_before();
+                mbar_arrive(&m_empty[mi]);
+            }
             if (wq == 0) TC_TS(1 + set, q * 5 + 2);
             if (un != NU - 1) continue;
             // ---------------- epilogue of tile `tile` -------------------------------------------
@@ -500,12 +572,21 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
             const bool rowok = trow < len;
             const size_t row = (size_t)(seg0 + (rowok ? trow : 0));
             const long long prow = prow_u + trow;
+            const int tr = min(128, len - t0), rl = wq * 32 + lane;     // tile-transposed tensors: rows of this tile, row inside it
+            const size_t tbase = (size_t)(seg0 + t0);
 #pragma unroll
             for (int cb = 0; cb < NC; cb += 16) {
                 float v[16];
                 tc_ld16(tcorr + cb, v);    // warp-collective: all lanes participate even for rows past the end
+                if (SU) {
+                    float m[16];
+                    tc_ld16(tmain + cb, m);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = racc[cb + j] + v[j];
+                    for (int j = 0; j < 16; ++j) v[j] = m[j] + v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = racc[cb + j] + v[j];
+                }
                 if (!rowok || (t.dbg & 2)) continue;
                 const int nb = nchunk * NCW + ccol + cb;
 #pragma unroll
@@ -528,28 +609,27 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                     }
                     if (t.yp.base && ob + 7 < t.yp.C) planes_store8(t.yp, prow, ob, o);
                 } else if (p.epi == EPI_RESSKIP) {
-                    // 16-column groups never straddle `split` (multiples of 16): x-update half or skip half
-                    const bool toX = nb < p.split;
-                    const int oc = toX ? nb : nb - p.split;
-                    float* d = toX ? p.y + row * p.ldy + oc : p.y2 + row * p.ldy2 + oc;
-                    const bool accum = toX || !p.y2_store;
-                    if (nb + 15 < p.Cout && ((p.split & 15) == 0) && ((((uintptr_t)d) & 15) == 0)) {
+                    // 16-column groups never straddle `split` (multiple of 16): x-update half or skip half
+                    const int nv = min(16, p.Cout - nb);
+                    if ((p.split & 15) == 0) {
+                        const bool toX = nb < p.split;
+                        const int oc = toX ? nb : nb - p.split;
+                        float* db = toX ? p.y : p.y2;
+                        const int ld = toX ? p.ldy : p.ldy2;
+                        const bool tt = toX ? t.y_tt : t.y2_tt;
                         // phase-separated read-modify-write: all loads, then the adds, then all stores
-                        if (accum) {
-                            float4 o4[4];
+                        if (SU) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) o4[q] = __ldcg(reinterpret_cast<const float4*>(d) + q);
+                            for (int j = 0; j < 16; ++j) v[j] = old[(SU ? cb : 0) + (SU ? j : 0)] + v[j];   // zeros where nothing accumulates
+                        } else if (toX || !p.y2_store) {
+                            float o[16];
+                            load16(db, ld, tt, row, tbase, tr, rl, oc, nv, o);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                v[4 * q] = o4[q].x + v[4 * q]; v[4 * q + 1] = o4[q].y + v[4 * q + 1];
-                                v[4 * q + 2] = o4[q].z + v[4 * q + 2]; v[4 * q + 3] = o4[q].w + v[4 * q + 3];
-                            }
+                            for (int j = 0; j < 16; ++j) v[j] = o[j] + v[j];
                         }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            __stcg(reinterpret_cast<float4*>(d) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                        store16(db, ld, tt, row, tbase, tr, rl, oc, nv, v);
                         const Planes& pl = toX ? t.yp : t.y2p;
-                        if (pl.base) { planes_store8(pl, prow, oc, v); planes_store8(pl, prow, oc + 8, v + 8); }
+                        if (pl.base && nv == 16) { planes_store8(pl, prow, oc, v); planes_store8(pl, prow, oc + 8, v + 8); }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -565,44 +645,38 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                         }
                     }
                 } else {
-                    float* d = t.write_f32 ? p.y + row * p.ldy + nb : nullptr;
-                    const float* rs = p.res ? p.res + row * p.ldr + nb : nullptr;
-                    const bool full = nb + 15 < p.Cout;
-                    const bool vec = full && (!d || ((((uintptr_t)d) & 15) == 0)) && (!rs || ((((uintptr_t)rs) & 15) == 0));
-                    if (vec) {
+                    const int nv = min(16, p.Cout - nb);
+                    if (p.res) {
+                        float r[16];
+                        load16(p.res, p.ldr, t.res_tt, row, tbase, tr, rl, nb, nv, r);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float4 w4 = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            if (rs) { const float4 r4 = reinterpret_cast<const float4*>(rs)[q]; w4.x += r4.x; w4.y += r4.y; w4.z += r4.z; w4.w += r4.w; }
-                            if (p.epi == EPI_RELU) { w4.x = fmaxf(w4.x, 0.f); w4.y = fmaxf(w4.y, 0.f); w4.z = fmaxf(w4.z, 0.f); w4.w = fmaxf(w4.w, 0.f); }
-                            else if (p.epi == EPI_ACCUM || p.epi == EPI_ACCUM_DIV) {
-                                const float4 o4 = reinterpret_cast<const float4*>(d)[q];
-                                w4.x = o4.x + w4.x; w4.y = o4.y + w4.y; w4.z = o4.z + w4.z; w4.w = o4.w + w4.w;
-                                if (p.epi == EPI_ACCUM_DIV) { w4.x /= p.div; w4.y /= p.div; w4.z /= p.div; w4.w /= p.div; }
-                            } else if (p.epi == EPI_TANH) { w4.x = tanh_ref(w4.x); w4.y = tanh_ref(w4.y); w4.z = tanh_ref(w4.z); w4.w = tanh_ref(w4.w); }
-                            if (d) reinterpret_cast<float4*>(d)[q] = w4;
-                            v[4 * q] = w4.x; v[4 * q + 1] = w4.y; v[4 * q + 2] = w4.z; v[4 * q + 3] = w4.w;
-                        }
-                        if (t.yp.base) {
-                            if (t.out_act == ACT_LEAKY) {
+                        for (int j = 0; j < 16; ++j) v[j] = v[j] + r[j];
+                    }
+                    if (p.epi == EPI_RELU) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * t.out_slope : v[j];
-                            }
-                            planes_store8(t.yp, prow, nb, v);
-                            planes_store8(t.yp, prow, nb + 8, v + 8);
-                        }
-                    } else {
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.epi == EPI_ACCUM || p.epi == EPI_ACCUM_DIV) {
+                        float a[16];
+                        if (t.acc_src) load16(t.acc_src, p.ldy, t.acc_tt, row, tbase, tr, rl, nb, nv, a);
+                        else load16(p.y, p.ldy, t.y_tt, row, tbase, tr, rl, nb, nv, a);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (nb + j >= p.Cout) continue;
-                            float w1 = v[j];
-                            if (rs) w1 = w1 + rs[j];
-                            if (p.epi == EPI_RELU) w1 = w1 < 0.f ? 0.f : w1;
-                            else if (p.epi == EPI_ACCUM) w1 = d[j] + w1;
-                            else if (p.epi == EPI_ACCUM_DIV) w1 = (d[j] + w1) / p.div;
-                            else if (p.epi == EPI_TANH) w1 = tanh_ref(w1);
-                            if (d) d[j] = w1;
+                        for (int j = 0; j < 16; ++j) v[j] = a[j] + v[j];
+                        if (p.epi == EPI_ACCUM_DIV) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] /= p.div;
                         }
+                    } else if (p.epi == EPI_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = tanh_ref(v[j]);
+                    }
+                    if (t.write_f32) store16(p.y, p.ldy, t.y_tt, row, tbase, tr, rl, nb, nv, v);
+                    if (t.yp.base && nv == 16) {
+                        if (t.out_act == ACT_LEAKY) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = v[j] < 0.f ? v[j] * t.out_slope : v[j];
+                        }
+                        planes_store8(t.yp, prow, nb, v);
+                        planes_store8(t.yp, prow, nb + 8, v + 8);
                     }
                 }
             }
@@ -638,6 +712,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                 }
             }
             tc_fence_before();
+            if (SU) mbar_arrive(&m_empty[mi]);
             mbar_arrive(&c_empty[ci]);
             if (wq == 0) TC_TS(1 + set, q * 5 + 4);
           }
@@ -842,6 +917,8 @@ struct TcOut {               // optional split-fp16 outputs requested from the e
     Planes yp, y2p;
     int out_act = ACT_NONE; float out_slope = 0.f;
     bool write_f32 = true;
+    bool y_tt = false, y2_tt = false, res_tt = false, acc_tt = false;
+    const float* acc_src = nullptr;
 };
 // Encodes the 3D tensor map of an activation's planes: (8, rows_p, 2*C/8), box (8, xr, KC/8).
 inline bool tc_make_map(CUtensorMap* m, const Planes& in, int xr, int KC) {
@@ -874,6 +951,8 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     t.xr = 128 + (p.k - 1) * p.dil;
     t.in_groups = in.C / 8;
     t.yp = out.yp; t.y2p = out.y2p; t.out_act = out.out_act; t.out_slope = out.out_slope; t.write_f32 = out.write_f32 ? 1 : 0;
+    t.y_tt = out.y_tt; t.y2_tt = out.y2_tt; t.res_tt = out.res_tt; t.acc_tt = out.acc_tt; t.acc_src = out.acc_src;
+    if ((t.y_tt && p.ldy != p.Cout && p.epi != EPI_RESSKIP) || (t.res_tt && !p.res)) return -2;   // TT tensors are dense
     const int ntiles = (maxlen + 127) / 128;
     // persistent CTAs, one per SM, walk the flat (utterance, tile, column chunk) grid round-robin: no wave quantisation,
     // TMEM allocation / barrier setup / resident weights paid once per SM.  The CTA count is a multiple of nchunks so
@@ -882,16 +961,24 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     const long long W = (long long)ntiles * nseg * w.nchunks;
     if (W <= 0 || W > 0x7fffffffLL) return -1;
     typedef void (*Kern)(const ConvP, const TcP, const CUtensorMap);
-    static const Kern kerns[9] = {conv_tc_kernel<1, 0, 0>, conv_tc_kernel<2, 0, 0>, conv_tc_kernel<3, 0, 0>, conv_tc_kernel<4, 0, 0>,
+    static const Kern kerns[10] = {conv_tc_kernel<1, 0, 0>, conv_tc_kernel<2, 0, 0>, conv_tc_kernel<3, 0, 0>, conv_tc_kernel<4, 0, 0>,
                                   conv_tc_kernel<1, 0, 1>, conv_tc_kernel<2, 0, 1>, conv_tc_kernel<3, 0, 1>, conv_tc_kernel<4, 0, 1>,
-                                  conv_tc_kernel<4, 1, 0>};
+                                  conv_tc_kernel<4, 1, 0>, conv_tc_kernel<4, 1, 0, 1>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 9; ++i) cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int i = 0; i < 10; ++i) cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     const int nct = std::min(4, w.NC / 16);
-    const int ki = w.colsplit ? 8 : (w.merge ? 4 : 0) + nct - 1;
+    // single-unit tiles (same formulas as the kernel): column-split layers whose whole K fits one promotion unit
+    bool single = false;
+    if (w.colsplit) {
+        const int upt = std::max(1, 12 / (w.KC / 16));
+        const int uu = (p.k + upt - 1) / upt;
+        if (uu == 1) { const int cpu = std::max(1, 12 / (p.k * (w.KC / 16))); single = (w.kchunks + cpu - 1) / cpu == 1; }
+    }
+    static const int env_su = getenv("STTS_TC_SU") ? atoi(getenv("STTS_TC_SU")) : 1;
+    const int ki = w.colsplit ? ((single && env_su) ? 9 : 8) : (w.merge ? 4 : 0) + nct - 1;
     const Kern kern = kerns[ki];
     // CTAs per SM: registers / shared memory (occupancy query) and TMEM columns (a CTA that could not allocate would
     // block until a co-resident persistent CTA has finished its whole stream)
@@ -903,7 +990,7 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
             if (small.smem <= 112 * 1024) budget = 110 * 1024;
         }
         const TcPlan pl0 = tc_plan(w, p.k, p.dil, true, budget);
-        static int regs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        static int regs[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (!regs[ki]) {
             cudaFuncAttributes fa;
             regs[ki] = (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 255;

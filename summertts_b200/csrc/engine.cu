@@ -92,6 +92,9 @@ struct ConvOpts {
     Planes* out2_planes = nullptr;       // EPI_RESSKIP: planes of the skip destination
     int out_act = ACT_NONE; float out_slope = 0.f;
     bool write_f32 = true;               // false: planes only (the fp32 tensor has no other reader)
+    // tile-transposed fp32 tensors (conv_tc.cuh, TcP): private to tensor-core epilogues
+    bool y_tt = false, y2_tt = false, res_tt = false, acc_tt = false;
+    const float* acc_src = nullptr;      // EPI_ACCUM(_DIV): accumulate onto this tensor instead of y
 #endif
 };
 
@@ -410,14 +413,17 @@ struct stts_engine {
             if (o.out_planes) out.yp = *o.out_planes;
             if (o.out2_planes) out.y2p = *o.out2_planes;
             out.out_act = o.out_act; out.out_slope = o.out_slope; out.write_f32 = o.write_f32;
+            out.y_tt = o.y_tt; out.y2_tt = o.y2_tt; out.res_tt = o.res_tt; out.acc_tt = o.acc_tt; out.acc_src = o.acc_src;
             const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream);
+            if (r == -2) throw std::runtime_error("tile-transposed tensor with a row stride (planning bug)");
             if (r < 0) throw CudaError("cuTensorMapEncodeTiled failed for an activation plane");
             launches += r;
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) throw CudaError(std::string("tc conv launch failed: ") + cudaGetErrorString(e));
             return;
         }
-        if (!o.write_f32 || o.in_planes) throw std::runtime_error("planes-only tensor routed to a non-tensor-core conv (planning bug)");
+        if (!o.write_f32 || o.in_planes || o.y_tt || o.y2_tt || o.res_tt || o.acc_src)
+            throw std::runtime_error("planes-only / tile-transposed tensor routed to a non-tensor-core conv (planning bug)");
 #endif
         const int halo = (c.k - 1) * c.dil;
         if (c.Cout <= 8 && o.epi != EPI_GATE && o.epi != EPI_RESSKIP) {
@@ -894,7 +900,7 @@ void stts_engine::run() {
         int rr = 1;
         for (size_t i = 0; i < ups.size(); ++i) {
             rr *= upRates[i];
-            need += ((size_t)Ft * rr * stageC[i] * 4 + 256) * 4;
+            need += ((size_t)Ft * rr * stageC[i] * 4 + 256) * 5;                                  // xx / t1 / xa / accb / accT
             need += 3 * (((size_t)Ft * rr + 2 * (size_t)B * 64 + 256) * stageC[i] * 4 + 256);   // planes xx / t1 / xa
         }
         if (decType != 0) {
@@ -956,7 +962,8 @@ void stts_engine::run() {
         {
             ConvOpts po;
 #ifdef STTS_WITH_TC
-            if (flowTc) po.out_planes = &hP;       // h feeds the k5 in-layer as planes
+            if (flowTc) { po.out_planes = &hP; po.y_tt = true; }   // h feeds the k5 in-layer as planes; its fp32 copy is
+                                                                   // only ever touched by the res_skip epilogues
 #endif
             conv(L.pre, x0, inter, hbuf, WH, fseg, B, maxF, po);                 // h = pre(x0)
         }
@@ -971,6 +978,7 @@ void stts_engine::run() {
             if (flowTc) {
                 g.in_planes = &hP; g.out_planes = &actsP; g.write_f32 = false;   // acts only ever feed res_skip
                 r.in_planes = &actsP;
+                r.y_tt = true; r.y2_tt = true;           // h / skip fp32: tile-transposed (coalesced read-modify-write)
                 if (l < nl - 1) r.out_planes = &hP;      // refreshed h for the next in-layer
                 else r.out2_planes = &skipP;             // finished skip sum feeds `post`
             }
@@ -1010,6 +1018,7 @@ void stts_engine::run() {
         float* t1 = ws.get<float>(rows * C);
         float* xa = ws.get<float>(rows * C);
         float* accb = ws.get<float>(rows * C);
+        float* accT = nullptr;                   // tensor path: MRF partial sums, tile-transposed
         {   // leaky(0.1) + ConvTranspose1d (phase-expanded): Generator_MS.cpp:172-175
             ConvOpts o; o.in_act = ACT_LEAKY; o.in_slope = 0.1f;
             curCls = STTS_CLS_DEC_UP; curRowsTotal = (int64_t)Ft * rate_in;
@@ -1027,6 +1036,7 @@ void stts_engine::run() {
         }
         if (rbTc) {
             xxP = arena_planes(curRowsTotal, B, C); t1P = arena_planes(curRowsTotal, B, C); xaP = arena_planes(curRowsTotal, B, C);
+            if (nRbK > 1) accT = ws.get<float>(rows * C);
             // leaky(0.1)(xx) once for the three ResBlock1 branches (ResBlock1.cpp:61)
             dim3 g(((size_t)(ml + 2 * TC_GAP) * (C / 8) + 255) / 256, B);
             split_planes_kernel<<<g, 256, 0, stream>>>(xx, C, sseg, C, ACT_LEAKY, 0.1f, xxP);
@@ -1048,15 +1058,24 @@ void stts_engine::run() {
                     o1.write_f32 = false;
                     o2.in_planes = &t1P;
                     if (!last) { o2.out_planes = &xaP; o2.out_act = ACT_LEAKY; o2.out_slope = 0.1f; }
+                    // xa (the ResBlock's running x) is only read and written by conv2 epilogues: tile-transposed
+                    o2.res_tt = b > 0;
+                    o2.y_tt = !last;
                 }
 #endif
                 conv(rb.c1[b], src, C, t1, C, sseg, B, ml, o1);
                 float* dst = xa;
                 if (last) {
                     dst = accb;
-                    if (j == 0) o2.epi = (nRbK == 1) ? EPI_STORE : EPI_STORE;
+                    if (j == 0) o2.epi = EPI_STORE;
                     else if (j < nRbK - 1) o2.epi = EPI_ACCUM;
                     else { o2.epi = EPI_ACCUM_DIV; o2.div = (float)nRbK; }
+#ifdef STTS_WITH_TC
+                    if (rbTc && accT) {          // partial sums live tile-transposed in accT; the last branch writes row-major accb
+                        if (j < nRbK - 1) { dst = accT; o2.y_tt = true; }
+                        else { o2.acc_src = accT; o2.acc_tt = true; }
+                    }
+#endif
                 }
                 conv(rb.c2[b], t1, C, dst, C, sseg, B, ml, o2);
             }
