@@ -491,8 +491,13 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
           const long long prow_u = it.prow_u;
           const int nchunk = it.z;
           const int ntiles_u = (len + 127) >> 7;
-          float* sb = sbias + (set * 2 + (jl & 1)) * NC;
-          if (tset < NC) {        // bias (+ speaker vector) of this tile's columns; published by the set's named barrier
+          // bias (+ speaker vector) of this tile's columns, published by the set's named barrier.  The column chunk is
+          // fixed per CTA, so without a per-utterance vector the first tile's copy serves the whole stream (no
+          // per-tile barrier coupling the set's four warps); with one, the copy is double-buffered per tile.
+          const bool zfix = (gridDim.x % t.nchunks) == 0;
+          const bool reload = jl == 0 || p.gvec != nullptr || !zfix;
+          float* sb = sbias + (set * 2 + ((p.gvec != nullptr || !zfix) ? (jl & 1) : 0)) * NC;
+          if (reload && tset < NC) {
               const int n = nchunk * NCW + ccol + tset;
               float bv = 0.f;
               if (n < p.Cout) {
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
               }
               sb[tset] = bv;
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
+          if (reload) asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory");
           float old[SU ? NC : 1];
           if (SU && p.epi == EPI_RESSKIP) {       // old h / skip values of this thread's row: in flight during the MMAs
               const int t0p = it.x * 128, trp = min(128, len - t0p), rlp = wq * 32 + lane;
@@ -572,20 +577,34 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
             const bool rowok = trow < len;
             const size_t row = (size_t)(seg0 + (rowok ? trow : 0));
             const long long prow = prow_u + trow;
-            const int tr = min(128, len - t0), rl = wq * 32 + lane;     // tile-transposed tensors: rows of this tile, row inside it
+            const int trw = min(128, len - t0), rl = wq * 32 + lane;     // tile-transposed tensors: rows of this tile, row inside it
             const size_t tbase = (size_t)(seg0 + t0);
+            if (!SU) {
+                // fold the correction accumulator into the registers first and hand it back at once: the next tile's
+                // correction MMAs then overlap this tile's global-memory epilogue (warp-collective TMEM loads: all
+                // lanes participate even for rows past the end)
+#pragma unroll
+                for (int cb = 0; cb < NC; cb += 16) {
+                    float v[16];
+                    tc_ld16(tcorr + cb, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
+                }
+                tc_fence_before();
+                mbar_arrive(&c_empty[ci]);
+            }
 #pragma unroll
             for (int cb = 0; cb < NC; cb += 16) {
                 float v[16];
-                tc_ld16(tcorr + cb, v);    // warp-collective: all lanes participate even for rows past the end
                 if (SU) {
                     float m[16];
+                    tc_ld16(tcorr + cb, v);
                     tc_ld16(tmain + cb, m);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = m[j] + v[j];
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = racc[cb + j] + v[j];
+                    for (int j = 0; j < 16; ++j) v[j] = racc[cb + j];
                 }
                 if (!rowok || (t.dbg & 2)) continue;
                 const int nb = nchunk * NCW + ccol + cb;
@@ -623,11 +642,11 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                             for (int j = 0; j < 16; ++j) v[j] = old[(SU ? cb : 0) + (SU ? j : 0)] + v[j];   // zeros where nothing accumulates
                         } else if (toX || !p.y2_store) {
                             float o[16];
-                            load16(db, ld, tt, row, tbase, tr, rl, oc, nv, o);
+                            load16(db, ld, tt, row, tbase, trw, rl, oc, nv, o);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = o[j] + v[j];
                         }
-                        store16(db, ld, tt, row, tbase, tr, rl, oc, nv, v);
+                        store16(db, ld, tt, row, tbase, trw, rl, oc, nv, v);
                         const Planes& pl = toX ? t.yp : t.y2p;
                         if (pl.base && nv == 16) { planes_store8(pl, prow, oc, v); planes_store8(pl, prow, oc + 8, v + 8); }
                     } else {
@@ -648,7 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                     const int nv = min(16, p.Cout - nb);
                     if (p.res) {
                         float r[16];
-                        load16(p.res, p.ldr, t.res_tt, row, tbase, tr, rl, nb, nv, r);
+                        load16(p.res, p.ldr, t.res_tt, row, tbase, trw, rl, nb, nv, r);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = v[j] + r[j];
                     }
@@ -657,8 +676,8 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     } else if (p.epi == EPI_ACCUM || p.epi == EPI_ACCUM_DIV) {
                         float a[16];
-                        if (t.acc_src) load16(t.acc_src, p.ldy, t.acc_tt, row, tbase, tr, rl, nb, nv, a);
-                        else load16(p.y, p.ldy, t.y_tt, row, tbase, tr, rl, nb, nv, a);
+                        if (t.acc_src) load16(t.acc_src, p.ldy, t.acc_tt, row, tbase, trw, rl, nb, nv, a);
+                        else load16(p.y, p.ldy, t.y_tt, row, tbase, trw, rl, nb, nv, a);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = a[j] + v[j];
                         if (p.epi == EPI_ACCUM_DIV) {
@@ -669,7 +688,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = tanh_ref(v[j]);
                     }
-                    if (t.write_f32) store16(p.y, p.ldy, t.y_tt, row, tbase, tr, rl, nb, nv, v);
+                    if (t.write_f32) store16(p.y, p.ldy, t.y_tt, row, tbase, trw, rl, nb, nv, v);
                     if (t.yp.base && nv == 16) {
                         if (t.out_act == ACT_LEAKY) {
 #pragma unroll
@@ -711,9 +730,11 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                     }
                 }
             }
-            tc_fence_before();
-            if (SU) mbar_arrive(&m_empty[mi]);
-            mbar_arrive(&c_empty[ci]);
+            if (SU) {
+                tc_fence_before();
+                mbar_arrive(&m_empty[mi]);
+                mbar_arrive(&c_empty[ci]);
+            }
             if (wq == 0) TC_TS(1 + set, q * 5 + 4);
           }
           ++jl;
@@ -1013,7 +1034,8 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     static long long* trace_buf = nullptr;
     static const int env_trace = getenv("STTS_TC_TRACE") ? atoi(getenv("STTS_TC_TRACE")) : 0;
     static int trace_left = 2;
-    const bool do_trace = env_trace && (env_trace == 1 || (env_trace == 2 && p.epi == EPI_RESSKIP && trace_left > 0 && maxlen > 256));
+    const bool do_trace = env_trace && (env_trace == 1 || (env_trace == 2 && p.epi == EPI_RESSKIP && trace_left > 0 && maxlen > 256) ||
+                                        (env_trace == 3 && p.res && p.Cout == 32 && p.k == 7 && trace_left > 0));
     if (do_trace && !trace_buf) { cudaMalloc(&trace_buf, 5 * 1024 * 8); }
     if (do_trace) cudaMemsetAsync(trace_buf, 0, 5 * 1024 * 8, stream);
     t.trace = do_trace ? trace_buf : nullptr;
