@@ -297,6 +297,10 @@ def main():
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1),
                 "algorithmic_flops_per_launch": d["flops"] / max(d["launches"], 1),
                 "share_of_conv_time": d["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
+        if traffic:   # measured DRAM bytes per launch (ncu) over the live launch time: the class's HBM utilisation
+            gbs = traffic / (roof["avg_launch_ms"] * 1e-3) / 1e9
+            roof["hbm_view"] = {"achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                                "note": "ncu dram bytes per launch / live launch time"}
 
     # ---- single-utterance latency (BASELINE config 2 shape), informational ------------------------
     single = None
