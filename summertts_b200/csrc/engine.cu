@@ -269,6 +269,8 @@ struct stts_engine {
         return d;
     }
 
+    int tc_usteps = 4;   // promotion unit (MMA steps) for the layers built next: 4 for token-level layers, 8 from the flow on
+
     // Build a dense conv in device layout [k][Cin'][CoutW'] from a file record W[o][k][c].
     // omap[new_o] = orig_o, cmap[new_c] = orig_c (identity when empty); sign scales w and b.
     DConv make_conv(const ConvRec& r, const std::vector<int>& omap = {}, const std::vector<int>& cmap = {},
@@ -299,7 +301,7 @@ struct stts_engine {
             d.b = upload(b);
         }
 #ifdef STTS_WITH_TC
-        if (tc_ok) tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned);
+        if (tc_ok) tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
 #else
         (void)tc_ok;
 #endif
@@ -340,7 +342,7 @@ struct stts_engine {
             d.b = upload(b);
         }
 #ifdef STTS_WITH_TC
-        tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned);
+        tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
 #endif
         return d;
     }
@@ -512,7 +514,7 @@ void stts_engine::build(const Model& M) {
             d.w = upload(w); d.b = upload(b);
             d.macs_row = (double)d.Cout * d.Cin;
 #ifdef STTS_WITH_TC
-            tc_prepare_weights(d.tc, w.data(), 1, d.Cin, d.Cout, d.CoutW, owned);
+            tc_prepare_weights(d.tc, w.data(), 1, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
 #endif
             L.qkv = d;
         }
@@ -562,6 +564,7 @@ void stts_engine::build(const Model& M) {
     // --- flow (ResidualCouplingBlock.cpp:29-39).  The channel flip before every layer
     // (ResidualCouplingBlock.cpp:66, nn_flip.cpp) is folded into the pre/post weights: at odd flip
     // parity logical channel c lives at physical channel C-1-c.
+    tc_usteps = 8;       // frame-level layers from here on (conv_tc.cuh, TcWeights::usteps)
     flowN = M.flow.nFlows; wnLayers = M.flow.nLayers;
     const int half = inter / 2;
     for (int i = 0; i < flowN; ++i) {
