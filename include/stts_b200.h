@@ -131,7 +131,7 @@ int64_t stts_kernel_launches(const stts_engine* e);
 void* stts_stream(const stts_engine* e);
 
 /* Conv path selection: 0 = fp32 CUDA-core tiles everywhere, 1 = tcgen05 tensor-core tiles
- * (split-bf16, fp32-accurate) where a layer is eligible.  Default 1 when the build has it. */
+ * (split-fp16, fp32-accurate) where a layer is eligible.  Default 1 when the build has it. */
 int stts_set_tensor_path(stts_engine* e, int32_t mode);
 
 /* Op-level test hook (tests only): runs ONE conv1d record (file format of nn_conv1d.cpp:25-52, or the

@@ -16,7 +16,7 @@
 //    (16 B per row) — no im2col, no per-tap reload, no zero-stuffed dilated kernel (the reference
 //    materialises both: nn_conv1d.cpp:133-155,184-187).
 //  * B operand: weights pre-packed on the host into the identical core-matrix layout, streamed from
-//    L2 by the bulk-copy engine (cp.async.bulk -> mbarrier complete_tx) through a 3-stage ring.
+//    L2 by the bulk-copy engine (cp.async.bulk -> mbarrier complete_tx) through a ring, or kept resident.
 //  * fp32 accuracy on fp16 tensor cores: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) for both
 //    operands; three MMAs per K-step (hi*hi, lo*hi, hi*lo) accumulate in fp32 (dropped lo*lo term is
 //    2^-22 relative).  Activations are pre-scaled by 2^3 and each layer's weights by 2^k (largest
@@ -25,14 +25,11 @@
 //    conversions saturate instead of overflowing.
 //  * accumulation accuracy: the tensor core's fp32 accumulator truncates on every MMA (measured here:
 //    a K=704 reduction lands 8x further from exact than fp32 FFMA, biased toward zero), so the hi*hi
-//    partial sums are PROMOTED to fp32 registers after every K-chunk (<= 22 MMA steps): the loader
-//    warps drain the `main` TMEM accumulator (tcgen05.ld, round-to-nearest adds) while they refill the
-//    A tile, and the next chunk restarts it with accumulate = 0.  The lo*hi / hi*lo correction terms
-//    (2^-11 of the magnitude) accumulate in a second TMEM accumulator for the whole tile.
-//  * warp roles: warps 0-3 promote partial sums and run the epilogue (tcgen05.ld -> bias / gate /
-//    residual / ... -> fp32 rows and/or split-fp16 planes for the next conv); warp 4 lane 0 issues the
-//    MMAs; warp 5 lane 0 streams weights; warp 6 lane 0 streams activation tiles (TMA).  mbarriers
-//    connect them; tcgen05.commit releases smem stages.
+//    partial sums are PROMOTED to fp32 registers every `usteps` MMA steps (a promotion unit; 8 steps,
+//    4 for token-level layers): the epilogue warps drain the `main` TMEM accumulator (tcgen05.ld,
+//    round-to-nearest adds) and the next unit restarts it with accumulate = 0.  The lo*hi / hi*lo
+//    correction terms (2^-11 of the magnitude) accumulate in a second TMEM accumulator for the whole tile.
+//  * persistent CTAs and warp roles: see the block comment above conv_tc_kernel.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -80,9 +77,8 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     static const int env_us = getenv("STTS_TC_USTEPS") ? atoi(getenv("STTS_TC_USTEPS")) : 0;
     t.usteps = env_us > 0 ? env_us : (usteps > 0 ? usteps : 8);
     if (Cin % 16 != 0 || Cout < 16 || k > 16) return;
-    // K-chunk: one promotion per chunk
-    // 64-channel chunks halve the per-stage barrier traffic of the MMA issuer (measured: 153 -> ~90 cycles per MMA);
-    // promotion period = 4*k MMA steps (<= 44), still far inside the accuracy budget (tools/tc_error.py)
+    // K-chunk = one TMA box / weight stage per tap.  64-channel chunks halve the per-stage barrier traffic of the MMA
+    // issuer (measured: 153 -> ~90 cycles per MMA); promotion happens per unit of `usteps` MMA steps inside the chunk
     static const int env_kc64 = getenv("STTS_TC_KC64") ? atoi(getenv("STTS_TC_KC64")) : 1;
     const int KC = (Cin % 64 == 0 && (env_kc64 == 1 || (env_kc64 == 2 && k <= 5))) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
     const int Cr = (Cout + 15) & ~15;

@@ -55,7 +55,7 @@ struct DConv {
     int Cin = 0, Cout = 0, CoutW = 0, k = 1, dil = 1, padl = 0;
     double macs_row = 0;  // algorithmic MACs per input-rate row (un-expanded taps, live outputs only)
 #ifdef STTS_WITH_TC
-    TcWeights tc;        // split-bf16 UMMA-layout copy (filled when the layer is tensor-path eligible)
+    TcWeights tc;        // split-fp16 UMMA-layout copy (filled when the layer is tensor-path eligible)
 #endif
 };
 struct DLN {
@@ -1155,7 +1155,7 @@ extern "C" {
 const char* stts_last_error(void) { return g_last_error.c_str(); }
 const char* stts_version(void) {
 #ifdef STTS_WITH_TC
-    return "stts_b200 0.1 (sm_100a; fp32 FFMA tiles + tcgen05 split-bf16 tiles)";
+    return "stts_b200 0.1 (sm_100a; fp32 FFMA tiles + tcgen05 split-fp16 tiles)";
 #else
     return "stts_b200 0.1 (sm_100a; fp32 FFMA tiles)";
 #endif
