@@ -143,6 +143,13 @@ int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_float
                      int pad_override, int dil_override, const float* x, int T, int nseg, const int* seg_off,
                      int in_act, float slope, int epi, float** y, int* rows, int* cols);
 
+/* Host-only test hook: packs one conv's weights W[outCh][k][inCh] (the record order of nn_conv1d.cpp:38-41) the way
+ * the tensor-core path stores them (split-fp16 hi/lo stages in UMMA core-matrix order, power-of-two pre-scale) -- no GPU
+ * needed; the CPU suite checks it against a numpy restatement of the layout.
+ * meta[9] = {eligible, NC, nchunks, KC, kchunks, colsplit, merged, usteps, weight exponent}; *halves is malloc'd. */
+int stts_debug_pack_weights(const float* w, int32_t k, int32_t inCh, int32_t outCh, int32_t usteps, int32_t* meta,
+                            uint16_t** halves, int64_t* n_halves);
+
 /* Replaces: tts_free_data, src/utils/utils.cpp:34-37. */
 void stts_free(void* p);
 

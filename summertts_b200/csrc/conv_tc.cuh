@@ -59,6 +59,7 @@ struct TcWeights {
     int merge = 0;             // 1 (single K-chunk layers): stage = [c8][hi rows | lo rows][8]; one N=2*NC MMA does hi*hi and hi*lo
     int nchunks = 0, kchunks = 0, KC = 0, taps = 0;
     float inv_scale = 1.f;     // 2^-(k+3): applied to the accumulator in the epilogue
+    int wexp = 0;              // weights are packed as w * 2^wexp
     int usteps = 8;            // MMA steps (K = 16 each) the hi*hi accumulator may run in TMEM before it is promoted to fp32
                                // registers.  Measured on single_speaker_mid (waveform rel-err vs the reference; fp32 FFMA
                                // path = 6.2e-4): <= 4 steps on 1x1 convs and <= 12 elsewhere 7.8e-4; 12 steps on the 1x1
@@ -71,12 +72,15 @@ struct TcWeights {
 // ---------------------------------------------------------------------------------------------
 // host: weight packing
 // ---------------------------------------------------------------------------------------------
-inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/, int k, int Cin, int Cout, int CoutW,
-                               std::vector<void*>& owned, int usteps = 0) {
+// Pure host part: chooses the tiling (NC, KC, column-split / merged mode), the power-of-two weight scale, and packs the
+// hi / lo fp16 stages in UMMA core-matrix order into `buf`.  Returns false when the layer is not tensor-path shaped.
+// (Checked on the CPU against a numpy restatement of the layout: tests/test_binfmt_abi.py::test_tc_weight_packing.)
+inline bool tc_pack_weights_host(TcWeights& t, const float* w /*[k][Cin][CoutW]*/, int k, int Cin, int Cout, int CoutW,
+                                 std::vector<__half>& buf, int usteps = 0) {
     t.ok = false;
     static const int env_us = getenv("STTS_TC_USTEPS") ? atoi(getenv("STTS_TC_USTEPS")) : 0;
     t.usteps = env_us > 0 ? env_us : (usteps > 0 ? usteps : 8);
-    if (Cin % 16 != 0 || Cout < 16 || k > 16) return;
+    if (Cin % 16 != 0 || Cout < 16 || k > 16) return false;
     // K-chunk = one TMA box / weight stage per tap.  64-channel chunks halve the per-stage barrier traffic of the MMA
     // issuer (measured: 153 -> ~90 cycles per MMA); promotion happens per unit of `usteps` MMA steps inside the chunk
     static const int env_kc64 = getenv("STTS_TC_KC64") ? atoi(getenv("STTS_TC_KC64")) : 1;
@@ -106,8 +110,9 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
     e = std::max(-10, std::min(e, 20));
     const float ws = std::ldexp(1.0f, e);
     t.inv_scale = std::ldexp(1.0f, -e) / TC_ASCALE;
+    t.wexp = e;
     const size_t stage = (size_t)2 * KC * NC;  // halves per (nchunk, kchunk, tap)
-    std::vector<__half> buf((size_t)t.nchunks * t.kchunks * k * stage);
+    buf.assign((size_t)t.nchunks * t.kchunks * k * stage, __float2half_rn(0.f));
     for (int nc = 0; nc < t.nchunks; ++nc)
         for (int kc = 0; kc < t.kchunks; ++kc)
             for (int tap = 0; tap < k; ++tap) {
@@ -129,6 +134,12 @@ inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/,
                         }
                     }
             }
+    return true;
+}
+inline void tc_prepare_weights(TcWeights& t, const float* w /*[k][Cin][CoutW]*/, int k, int Cin, int Cout, int CoutW,
+                               std::vector<void*>& owned, int usteps = 0) {
+    std::vector<__half> buf;
+    if (!tc_pack_weights_host(t, w, k, Cin, Cout, CoutW, buf, usteps)) return;
     void* d = nullptr;
     if (cudaMalloc(&d, buf.size() * sizeof(__half)) != cudaSuccess) return;
     owned.push_back(d);

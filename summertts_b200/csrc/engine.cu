@@ -1356,6 +1356,36 @@ int stts_profile_fetch(const stts_engine* e, double* ms, double* flops, int64_t*
 
 // Op-level test hook: one conv (or ConvTranspose1d) through the FFMA tiles (use_tc == 0) or the
 // tcgen05 path (use_tc == 1) on caller-provided data.  x: [T][Cin] with optional utterance offsets.
+int stts_debug_pack_weights(const float* w, int32_t k, int32_t Cin, int32_t Cout, int32_t usteps, int32_t* meta,
+                            uint16_t** halves, int64_t* n_halves) {
+    return guard([&]() {
+#ifdef STTS_WITH_TC
+        if (!w || !meta || !halves || !n_halves || k < 1 || Cin < 1 || Cout < 1) throw std::invalid_argument("bad argument");
+        // file order W[o][k][c] -> device order [k][Cin][CoutW]
+        const int CoutW = (Cout + 3) & ~3;
+        std::vector<float> dw((size_t)k * Cin * CoutW, 0.f);
+        for (int o = 0; o < Cout; ++o)
+            for (int t = 0; t < k; ++t)
+                for (int c = 0; c < Cin; ++c) dw[((size_t)t * Cin + c) * CoutW + o] = w[((size_t)o * k + t) * Cin + c];
+        TcWeights tw;
+        std::vector<__half> buf;
+        const bool ok = tc_pack_weights_host(tw, dw.data(), k, Cin, Cout, CoutW, buf, usteps);
+        meta[0] = ok ? 1 : 0; meta[1] = tw.NC; meta[2] = tw.nchunks; meta[3] = tw.KC; meta[4] = tw.kchunks;
+        meta[5] = tw.colsplit; meta[6] = tw.merge; meta[7] = tw.usteps; meta[8] = tw.wexp;
+        *n_halves = (int64_t)buf.size();
+        *halves = nullptr;
+        if (ok && !buf.empty()) {
+            *halves = (uint16_t*)malloc(buf.size() * 2);
+            if (!*halves) throw std::bad_alloc();
+            memcpy(*halves, buf.data(), buf.size() * 2);
+        }
+#else
+        (void)w; (void)k; (void)Cin; (void)Cout; (void)usteps; (void)meta; (void)halves; (void)n_halves;
+        throw Unsupported("built without the tensor-core path");
+#endif
+    });
+}
+
 int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_floats, int transposed, int stride,
                      int pad_override, int dil_override, const float* x, int T, int nseg, const int* seg_off,
                      int in_act, float slope, int epi, float** y, int* rows, int* cols) {

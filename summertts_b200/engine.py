@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
-    "stts_test_conv1d",
+    "stts_test_conv1d", "stts_debug_pack_weights",
 ]
 
 _lib = None
@@ -71,6 +71,7 @@ def load_library():
     L.stts_profile_fetch.argtypes = [vp, vp, vp, vp]
     L.stts_test_conv1d.argtypes = [C.c_int, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp,
                                    C.c_int, f32, C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.stts_debug_pack_weights.argtypes = [vp, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(i64)]
     L.stts_kernel_launches.argtypes = [vp]
     L.stts_kernel_launches.restype = i64
     L.stts_stream.argtypes = [vp]
@@ -256,6 +257,23 @@ def test_conv1d(rec, x, use_tc=0, transposed=False, stride=1, pad=-1, dil=0, seg
     out = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_float)), shape=(n,)).copy().reshape(r.value, c.value)
     L.stts_free(y)
     return out
+
+
+def debug_pack_weights(w, usteps=0):
+    """Host-only hook: tensor-path packing of one conv's weights W[outCh][k][inCh] -> (meta dict, uint16 fp16 bit patterns)."""
+    L = load_library()
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    o, k, c = w.shape
+    meta = np.zeros(9, np.int32)
+    h, n = C.c_void_p(), C.c_int64()
+    _check(L.stts_debug_pack_weights(w.ctypes.data, k, c, o, int(usteps), meta.ctypes.data, C.byref(h), C.byref(n)))
+    names = ["eligible", "NC", "nchunks", "KC", "kchunks", "colsplit", "merged", "usteps", "wexp"]
+    md = {a: int(b) for a, b in zip(names, meta)}
+    if not h.value:
+        return md, np.zeros(0, np.uint16)
+    out = np.ctypeslib.as_array(C.cast(h, C.POINTER(C.c_uint16)), shape=(n.value,)).copy()
+    L.stts_free(h)
+    return md, out
 
 
 def ttsLoadModel(path: str) -> np.ndarray:

@@ -87,3 +87,58 @@ def test_create_fails_loudly_without_gpu(native_lib):
     assert b"no CUDA device" in native_lib.stts_last_error()
     with pytest.raises(engine.SttsError):
         engine.SynthesizerTrn(blob)
+
+
+@pytest.mark.parametrize("shape", [(384, 5, 192), (64, 7, 64), (32, 11, 32), (72, 7, 32), (192, 1, 96), (96, 1, 192), (20, 3, 48)])
+def test_tc_weight_packing(native_lib, shape):
+    """Host side of the tensor-core path (conv_tc.cuh, tc_pack_weights_host): tiling choice, power-of-two scale and the
+    split-fp16 UMMA core-matrix stage layout, against an independent numpy restatement.  Bit-exact."""
+    from summertts_b200 import engine
+
+    o, k, c = shape
+    rng = np.random.default_rng(o * 131 + k * 17 + c)
+    w = (rng.standard_normal(shape) * rng.uniform(0.01, 2.0)).astype(np.float32)
+    meta, halves = engine.debug_pack_weights(w)
+    assert meta["eligible"] == 1
+    NC, nch, KC, kch, merged = meta["NC"], meta["nchunks"], meta["KC"], meta["kchunks"], meta["merged"]
+    assert KC * kch == c and NC % 16 == 0 and NC * nch >= o and NC * (nch - 1) < o
+    assert meta["colsplit"] == (1 if (o >= 128 and KC == 64) else 0)
+    assert merged == (1 if (kch == 1 and not meta["colsplit"] and k * (KC // 16) <= 24) else 0)
+    # largest |w| * 2^e lands in [512, 1024): fp16-safe and far from the subnormal range
+    e = meta["wexp"]
+    assert 512.0 <= np.abs(w).max() * 2.0 ** e < 1024.0
+    v = (w * np.float32(2.0 ** e)).astype(np.float32)
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float32)).astype(np.float16)
+    # hi + lo reproduces the scaled weight to ~2^-22 relative
+    assert np.abs(hi.astype(np.float64) + lo.astype(np.float64) - v).max() <= np.abs(v).max() * 2.0 ** -21
+    stage = 2 * KC * NC
+    assert halves.size == nch * kch * k * stage
+    exp = np.zeros(halves.size, np.uint16)
+    hb, lb = hi.view(np.uint16), lo.view(np.uint16)
+    for nc in range(nch):
+        for kc in range(kch):
+            for tap in range(k):
+                base = ((nc * kch + kc) * k + tap) * stage
+                for cc in range(KC):
+                    n = np.arange(NC)
+                    oo = nc * NC + n
+                    ok = oo < o
+                    src_h = np.where(ok, hb[np.minimum(oo, o - 1), tap, kc * KC + cc], 0)
+                    src_l = np.where(ok, lb[np.minimum(oo, o - 1), tap, kc * KC + cc], 0)
+                    if merged:     # [c/8][hi rows 0..NC-1 | lo rows NC..2NC-1][c%8]
+                        ih = base + ((cc // 8) * 2 * NC + n) * 8 + cc % 8
+                        exp[ih] = src_h
+                        exp[ih + NC * 8] = src_l
+                    else:          # hi plane [c/8][n][c%8], then the lo plane
+                        ih = base + ((cc // 8) * NC + n) * 8 + cc % 8
+                        exp[ih] = src_h
+                        exp[ih + KC * NC] = src_l
+    assert np.array_equal(halves, exp)
+
+
+def test_tc_weight_packing_rejects_odd_shapes(native_lib):
+    from summertts_b200 import engine
+
+    assert engine.debug_pack_weights(np.ones((8, 3, 32), np.float32))[0]["eligible"] == 0     # < 16 output channels
+    assert engine.debug_pack_weights(np.ones((32, 3, 20), np.float32))[0]["eligible"] == 0    # inCh % 16 != 0
