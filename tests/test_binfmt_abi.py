@@ -142,3 +142,28 @@ def test_tc_weight_packing_rejects_odd_shapes(native_lib):
 
     assert engine.debug_pack_weights(np.ones((8, 3, 32), np.float32))[0]["eligible"] == 0     # < 16 output channels
     assert engine.debug_pack_weights(np.ones((32, 3, 20), np.float32))[0]["eligible"] == 0    # inCh % 16 != 0
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under summertts_b200/ (Python, CUDA, C++ host) and no product entry point may
+    import, link or execute it; bench.py may only in its CPU legs, __graft_entry__ only to build it and in smoke()."""
+    import re
+
+    pkg = os.path.join(ROOT, "summertts_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) in ("_build", "bin", "__pycache__"):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")) and f != "Makefile":
+                continue
+            txt = open(os.path.join(d, f), errors="replace").read()
+            if re.search(r"\boracle\b", txt):
+                bad.append(os.path.join(d, f))
+    assert not bad, "product files mention the oracle: %s" % bad
+    hdr = open(os.path.join(ROOT, "include", "stts_b200.h")).read()
+    assert "oracle" not in hdr
+    # bench.py: the oracle only inside the CPU legs (cpu_worker_steps / --impl reference)
+    for line in open(os.path.join(ROOT, "bench.py")):
+        if re.search(r"^\s*(from|import)\s+oracle", line):
+            raise AssertionError("bench.py imports the oracle at module level: " + line)
