@@ -9,12 +9,17 @@
 //                                                                  (one batched call per GPU; --concat: one file, in order)
 //   tts_b200 --ids <ids.txt> <model.bin> <out.wav>                 lines of phoneme ids instead of text (no frontend needed)
 //   options: --gpus N (one engine + one host thread per GPU, longest-first partition), --sid S, --length-scale L,
+//            --frontend-threads T (text -> ids on T host threads, one frontend instance each: at batch 64 the 3-4 ms/sentence
+//            host frontend, not the GPU, is the serial bottleneck -- SURVEY §8f rank 3), --dump-ids (frontend only: print the
+//            phoneme ids of every utterance, one line each, and stop -- no GPU needed; feeds `--ids` elsewhere),
 //            --selftest-wav <out.wav> (writes one second of a 440 Hz tone; container check without a GPU)
 //
 // Text input needs the host frontend (frontend.hpp; built with -DSTTS_WITH_REF_FRONTEND against the reference's sources by
 // `make REF=...`); the ids-only build has no dependency outside this repository.  No CPU fallback: without a usable
 // sm_100 device stts_create fails and the tool exits non-zero with the library's message.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -36,12 +41,13 @@ namespace {
 
 struct Args {
     std::string input, model, out;
-    bool ids = false, per_line = false, concat = false;
-    int gpus = 1, sid = -1;
+    bool ids = false, per_line = false, concat = false, dump_ids = false;
+    int gpus = 1, sid = -1, fe_threads = 0;
     float length_scale = -1.f;
 };
 
 struct Utt {
+    std::string text;
     std::vector<int32_t> ids;
     float ls = 1.f;
     int32_t sid = 0;
@@ -51,7 +57,8 @@ struct Utt {
 
 int usage(const char* argv0) {
     fprintf(stderr,
-            "usage: %s [--ids] [--per-line] [--concat] [--gpus N] [--sid S] [--length-scale L] <input.txt> <model.bin> <out.wav>\n"
+            "usage: %s [--ids] [--per-line] [--concat] [--dump-ids] [--gpus N] [--frontend-threads T] [--sid S] [--length-scale L]\n"
+            "          <input.txt> <model.bin> <out.wav>\n"
             "       %s --selftest-wav <out.wav>\n", argv0, argv0);
     return 2;
 }
@@ -126,7 +133,9 @@ int main(int argc, char** argv) {
         if (s == "--ids") a.ids = true;
         else if (s == "--per-line") a.per_line = true;
         else if (s == "--concat") a.concat = true;
+        else if (s == "--dump-ids") a.dump_ids = true;
         else if (s == "--gpus") a.gpus = std::max(1, atoi(need("--gpus")));
+        else if (s == "--frontend-threads") a.fe_threads = std::max(1, atoi(need("--frontend-threads")));
         else if (s == "--sid") a.sid = atoi(need("--sid"));
         else if (s == "--length-scale") a.length_scale = (float)atof(need("--length-scale"));
         else if (s == "--selftest-wav") {
@@ -174,31 +183,20 @@ int main(int argc, char** argv) {
     }
     if (texts.empty()) { fprintf(stderr, "no input\n"); return 1; }
 
-#ifdef STTS_WITH_REF_FRONTEND
-    stts::Frontend* fe = nullptr;
-    if (!a.ids) {
-        fe = stts::make_frontend(lang_type, const_cast<float*>(hdr), (int64_t)model.size(), nn_end);
-        if (!fe) { fprintf(stderr, "model has no frontend tail\n"); return 1; }
-    }
-#else
+#ifndef STTS_WITH_REF_FRONTEND
     if (!a.ids) { fprintf(stderr, "this build has no text frontend: pass --ids <file of phoneme ids> (or build with make REF=...)\n"); return 1; }
 #endif
 
     std::vector<Utt> utts;
     auto add = [&](const std::string& t, int sid, float ls, const std::string& out) -> bool {
         Utt u;
-        u.sid = sid; u.ls = ls; u.out = out;
+        u.text = t; u.sid = sid; u.ls = ls; u.out = out;
         if (a.ids) {
             std::istringstream is(t);
             long v;
             while (is >> v) u.ids.push_back((int32_t)v);
             if (!is.eof()) { fprintf(stderr, "bad id line: %s\n", t.c_str()); return false; }
-        } else {
-#ifdef STTS_WITH_REF_FRONTEND
-            if (!fe->text_to_ids(t, u.ids, u.ls)) { fprintf(stderr, "frontend produced no ids\n"); return false; }
-#endif
         }
-        if (u.ids.size() < 5) { fprintf(stderr, "utterance shorter than 5 ids (relative attention window)\n"); return false; }
         utts.push_back(std::move(u));
         return true;
     };
@@ -222,6 +220,49 @@ int main(int argc, char** argv) {
             const bool many = texts.size() > 1 && !a.concat;
             if (!add(texts[i], sid, ls_default, many ? numbered(a.out, "_%04d.wav", (int)i) : a.out)) return 1;
         }
+    }
+
+    // ---- text -> phoneme ids on the host: T threads, one frontend instance each (an instance is not re-entrant:
+    //      SynthesizerTrn.cpp:338 mutates a member per call), utterances handed out through an atomic counter -----------
+#ifdef STTS_WITH_REF_FRONTEND
+    if (!a.ids) {
+        int T = a.fe_threads > 0 ? a.fe_threads : (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+        // measured (8-core host, CHS model): building one frontend 1.15 s alone, ~2 s when several build at once; 3.65 ms per
+        // sentence -> an extra worker pays for itself from ~400 sentences on
+        T = (int)std::max<size_t>(1, std::min<size_t>(T, (utts.size() + 383) / 384));
+        std::atomic<size_t> next(0);
+        std::atomic<int> failed(0);
+        const bool verbose = getenv("STTS_CLI_VERBOSE") != nullptr;
+        auto worker = [&] {
+            const auto t0 = std::chrono::steady_clock::now();
+            stts::Frontend* fe = stts::make_frontend(lang_type, const_cast<float*>(hdr), (int64_t)model.size(), nn_end);
+            if (!fe) { failed = 2; return; }
+            const auto t1 = std::chrono::steady_clock::now();
+            size_t n = 0;
+            for (size_t i; (i = next.fetch_add(1)) < utts.size(); ++n)
+                if (!fe->text_to_ids(utts[i].text, utts[i].ids, utts[i].ls)) failed = 1;
+            const auto t2 = std::chrono::steady_clock::now();
+            delete fe;
+            if (verbose)
+                fprintf(stderr, "frontend worker: init %.2f s, %zu utterances in %.2f s\n", std::chrono::duration<double>(t1 - t0).count(), n,
+                        std::chrono::duration<double>(t2 - t1).count());
+        };
+        std::vector<std::thread> ft;
+        for (int t = 1; t < T; ++t) ft.emplace_back(worker);
+        worker();
+        for (auto& t : ft) t.join();
+        if (failed == 2) { fprintf(stderr, "model has no frontend tail\n"); return 1; }
+        if (failed) { fprintf(stderr, "frontend produced no ids\n"); return 1; }
+    }
+#endif
+    for (auto& u : utts)
+        if (u.ids.size() < 5) { fprintf(stderr, "utterance shorter than 5 ids (relative attention window)\n"); return 1; }
+    if (a.dump_ids) {
+        for (auto& u : utts) {
+            for (size_t i = 0; i < u.ids.size(); ++i) printf(i ? " %d" : "%d", u.ids[i]);
+            printf("\n");
+        }
+        return 0;
     }
 
     // ---- partition longest-first over the GPUs, one thread each --------------------------------------

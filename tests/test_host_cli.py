@@ -107,3 +107,35 @@ def test_cli_ids_batch_matches_c_abi(cli, tmp_path):
     allpcm = np.concatenate([tts.infer_ids(np.asarray(u, np.int32), 0, 1.0) for u in utts])
     assert raw[:44] == ref_header(2 * allpcm.size) and np.array_equal(np.frombuffer(raw[44:], dtype="<i2"), allpcm)
     tts.close()
+
+
+REF_CLI = os.path.join(HOST, "_build", "tts_b200")
+REF_ROOT = "/root/reference"
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.isdir(os.path.join(REF_ROOT, "models"))),
+                    reason="frontend-enabled tts_b200 needs the reference tree (make -C summertts_b200/host REF=...)")
+def test_cli_text_frontend_reproduces_reference_ids(tmp_path):
+    """Text -> ids through the CLI (reference frontend behind frontend.hpp) == the id sequence the reference's own
+    SynthesizerTrn::infer produces for test.txt (SURVEY.md §8c), English: 700 ids for test_eng.txt; several frontend
+    worker threads give the same ids as one."""
+    from parity_util import TEST_TXT_IDS
+
+    def dump(args):
+        r = subprocess.run([REF_CLI, "--dump-ids"] + args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return [[int(v) for v in l.split()] for l in r.stdout.splitlines() if l.strip()]
+
+    chs = os.path.join(REF_ROOT, "models", "single_speaker_fast.bin")
+    got = dump([os.path.join(REF_ROOT, "test.txt"), chs, str(tmp_path / "o.wav")])
+    assert got == [list(TEST_TXT_IDS)]
+    eng = dump([os.path.join(REF_ROOT, "test_eng.txt"), os.path.join(REF_ROOT, "models", "single_speaker_english_fast.bin"),
+                str(tmp_path / "o.wav")])
+    assert len(eng) == 1 and len(eng[0]) == 700
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("今天天气不错,我们一起去公园散步吧。\n会议将于2024年5月20日上午10点举行。\n银行的行长今天在银行门口行走。\n" * 4)
+    one = dump(["--per-line", "--frontend-threads", "1", str(corpus), chs, str(tmp_path / "o.wav")])
+    # the heuristic would pick 1 worker for 12 lines; exercise the parallel path with an explicit count on a longer file
+    corpus.write_text(corpus.read_text() * 70)      # 840 lines -> 3 workers allowed
+    many = dump(["--per-line", "--frontend-threads", "3", str(corpus), chs, str(tmp_path / "o.wav")])
+    assert len(one) == 12 and len(many) == 840 and many[:12] == one and many[12:24] == one
