@@ -107,6 +107,52 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_cores():
+    """Cores this process may really use: sched affinity ∩ the cgroup CPU quota (cpu.max / cfs_quota).
+    os.cpu_count() reports the box's cores even inside a cgroup-limited lease (round 1: 128 'cores' that
+    were a small slice -> 5x box-to-box swing of the reference arm)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:  # noqa: BLE001
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:  # noqa: BLE001
+            pass
+    if quota:
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:  # noqa: BLE001
+        pass
+    return "unknown"
+
+
+def run_cpu_best(model_file, n_ids, vocab, forced_per_id, cores, reps, warm_reps):
+    """Sweep the worker count over {cores/2, cores} (SMT siblings / memory bandwidth can make half the
+    logical cores faster) and keep the best whole-box throughput.  Returns (samples/s, workers, seconds, table)."""
+    best = None
+    table = {}
+    for w in sorted({max(1, cores // 2), cores}):
+        samples, sec = run_cpu(model_file, 1, n_ids, vocab, forced_per_id, w, reps, warm_reps)
+        table[str(w)] = samples / sec
+        if best is None or samples / sec > best[0]:
+            best = (samples / sec, w, sec)
+    return best[0], best[1], best[2], table
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,7 +206,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    ncpu = os.cpu_count() or 1
+    ncpu = host_cores()
 
     blob, wkind, mfile = get_model(args.model)
     from summertts_b200 import binfmt
@@ -179,16 +225,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        workers = max(1, ncpu)
-        samples, sec = run_cpu(mfile, 1, args.ids, vocab, forced_per_id, workers, args.steps, args.warmup)
-        v = samples / sec
+        v, workers, sec, table = run_cpu_best(mfile, args.ids, vocab, forced_per_id, ncpu, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "audio_samples_per_sec", "value": v, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic ids; %s weights" % wkind, "config": config, "rtf": SR / v,
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": workers, "kind": "reference",
+                                 "cores_allowed": ncpu, "cores_logical": os.cpu_count(), "cpu_model": cpu_model(),
+                                 "sweep_samples_per_s": table,
                                  "sample": "each step = %d single-thread processes x 1 utterance of the workload "
-                                           "(compiled unmodified reference objects, oracle/_ref)" % workers},
+                                           "(compiled unmodified reference objects, oracle/_ref); worker count swept "
+                                           "over {allowed/2, allowed}, best kept" % workers},
                 "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -319,11 +366,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            workers = max(1, ncpu)
-            samples, sec = run_cpu(mfile, 1, args.ids, vocab, forced_per_id, workers, 1, 0)
-            cpu = {"value": samples / sec, "unit": "samples/s", "cores": workers, "kind": "reference",
-                   "sample": "%d utterances of the workload (one per core, single-thread processes of the compiled "
-                             "unmodified reference objects), %.1f s" % (workers, sec)}
+            v_cpu, workers, sec, table = run_cpu_best(mfile, args.ids, vocab, forced_per_id, ncpu, 1, 0)
+            cpu = {"value": v_cpu, "unit": "samples/s", "cores": workers, "kind": "reference",
+                   "cores_allowed": ncpu, "cores_logical": os.cpu_count(), "cpu_model": cpu_model(),
+                   "sweep_samples_per_s": table,
+                   "sample": "%d utterances of the workload (one per worker, single-thread processes of the compiled "
+                             "unmodified reference objects), %.1f s; worker count swept over {allowed/2, allowed}" % (workers, sec)}
         except Exception as ex:  # noqa: BLE001
             cpu = {"value": None, "error": str(ex)}
 
