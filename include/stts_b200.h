@@ -131,8 +131,14 @@ int64_t stts_kernel_launches(const stts_engine* e);
 void* stts_stream(const stts_engine* e);
 
 /* Conv path selection: 0 = fp32 CUDA-core tiles everywhere, 1 = tcgen05 tensor-core tiles
- * (split-fp16, fp32-accurate) where a layer is eligible.  Default 1 when the build has it. */
+ * (split-fp16, fp32-accurate) where a layer is eligible (default when the build has it), 2 = throughput mode: as 1, but
+ * the fused ResBlock1-pair kernels issue ONE fp16 MMA per K-step (fp16 operands, fp32 accumulate; the residual stream
+ * keeps its split-fp16 precision).  Mode 2 trades the <= 1 LSB PCM parity of mode 1 for speed; tolerance in DESIGN.md. */
 int stts_set_tensor_path(stts_engine* e, int32_t mode);
+
+/* Batches that were recomputed on the fp32 FFMA tiles because an activation exceeded the range the split-fp16
+ * operands of the tensor path can represent (|x| > ~8000); 0 for every shipped model. */
+int64_t stts_tensor_fallbacks(const stts_engine* e);
 
 /* Op-level test hook (tests only): runs ONE conv1d record (file format of nn_conv1d.cpp:25-52, or the
  * ConvTranspose1d record of nn_conv1d_transposed.cpp:25-52 when transposed != 0) on x[T][inCh] through
@@ -142,6 +148,13 @@ int stts_set_tensor_path(stts_engine* e, int32_t mode);
 int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_floats, int transposed, int stride,
                      int pad_override, int dil_override, const float* x, int T, int nseg, const int* seg_off,
                      int in_act, float slope, int epi, float** y, int* rows, int* cols);
+
+/* Op-level test hook (tests only) of the fused ResBlock1 pair kernel (ResBlock1.cpp:55-69, one loop iteration):
+ * y = act(x + conv2(leaky_0.1(conv1(leaky_0.1(x))))) with conv1 = rec1 at dilation dil1 (pad = dil1 (k-1)/2), conv2 = rec2
+ * (dilation 1), act = leaky 0.1 when out_leaky else identity; x[T][C], C in {32, 64}; mode 0 accurate / 1 throughput.
+ * y is malloc'd [T][C].  *flags_out bit 0: an activation left the split-fp16 range. */
+int stts_test_rbpair(int device, int mode, const float* rec1, int64_t n1, const float* rec2, int64_t n2, int dil1, const float* x,
+                     int T, int nseg, const int* seg_off, int out_leaky, float** y, uint32_t* flags_out);
 
 /* Host-only test hook: packs one conv's weights W[outCh][k][inCh] (the record order of nn_conv1d.cpp:38-41) the way
  * the tensor-core path stores them (split-fp16 hi/lo stages in UMMA core-matrix order, power-of-two pre-scale) -- no GPU

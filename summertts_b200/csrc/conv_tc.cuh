@@ -76,7 +76,7 @@ struct TcWeights {
 // hi / lo fp16 stages in UMMA core-matrix order into `buf`.  Returns false when the layer is not tensor-path shaped.
 // (Checked on the CPU against a numpy restatement of the layout: tests/test_binfmt_abi.py::test_tc_weight_packing.)
 inline bool tc_pack_weights_host(TcWeights& t, const float* w /*[k][Cin][CoutW]*/, int k, int Cin, int Cout, int CoutW,
-                                 std::vector<__half>& buf, int usteps = 0) {
+                                 std::vector<__half>& buf, int usteps = 0, bool force_merge = false) {
     t.ok = false;
     static const int env_us = getenv("STTS_TC_USTEPS") ? atoi(getenv("STTS_TC_USTEPS")) : 0;
     t.usteps = env_us > 0 ? env_us : (usteps > 0 ? usteps : 8);
@@ -94,7 +94,7 @@ inline bool tc_pack_weights_host(TcWeights& t, const float* w /*[k][Cin][CoutW]*
         // wide layers: N = 128 MMAs (65 cycles each instead of 2 x 53, half the MMA count and A-tile traffic)
         NC = 128;
         t.colsplit = 1;
-    } else if (Cr == 64 && env_nc32) {
+    } else if (Cr == 64 && env_nc32 && !force_merge) {
         NC = 32;           // two 32-column chunks: the light (<= 85 register) kernels run two CTAs per SM
     } else if (Cr > 64) {  // split into equal chunks of <= 64 columns (multiple of 16): 64 fp32 register accumulators/thread
         int n = (Cr + 63) / 64;
@@ -103,6 +103,10 @@ inline bool tc_pack_weights_host(TcWeights& t, const float* w /*[k][Cin][CoutW]*
     t.NC = NC; t.nchunks = (Cr + NC - 1) / NC; t.KC = KC; t.kchunks = Cin / KC; t.taps = k;
     static const int env_mg = getenv("STTS_TC_MERGE") ? atoi(getenv("STTS_TC_MERGE")) : 1;
     t.merge = (t.kchunks == 1 && !t.colsplit && env_mg && k * (KC / 16) <= 24) ? 1 : 0;   // no mid-chunk promotion in merged mode
+    if (force_merge) {   // rb_fused.cuh: merged stages for any tap count (it promotes per unit itself); needs one K-chunk, one column chunk
+        if (t.kchunks != 1 || t.colsplit || t.nchunks != 1) return false;
+        t.merge = 1;
+    }
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)k * Cin * CoutW; ++i) mx = std::max(mx, std::fabs(w[i]));
     int e = 0;
@@ -978,8 +982,21 @@ inline bool tc_make_map(CUtensorMap* m, const Planes& in, int xr, int KC) {
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, in.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// Function attributes are per device: every engine calls this once on ITS device (stts_engine::device_setup), so that
+// engines on several GPUs of one process (tts_cli --gpus N) all get the raised dynamic shared-memory limit.
+inline cudaError_t tc_device_setup() {
+    typedef void (*Kern)(const ConvP, const TcP, const CUtensorMap);
+    const Kern kerns[10] = {conv_tc_kernel<1, 0, 0>, conv_tc_kernel<2, 0, 0>, conv_tc_kernel<3, 0, 0>, conv_tc_kernel<4, 0, 0>,
+                            conv_tc_kernel<1, 0, 1>, conv_tc_kernel<2, 0, 1>, conv_tc_kernel<3, 0, 1>, conv_tc_kernel<4, 0, 1>,
+                            conv_tc_kernel<4, 1, 0>, conv_tc_kernel<4, 1, 0, 1>};
+    for (int i = 0; i < 10; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, const TcOut& out, int nseg, int maxlen,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int sms_dev = 0) {
     TcP t;
     static const int env_span = getenv("STTS_TC_SPAN") ? atoi(getenv("STTS_TC_SPAN")) : 0;
     t.usteps = w.usteps; t.span = env_span;
@@ -996,18 +1013,14 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     // persistent CTAs, one per SM, walk the flat (utterance, tile, column chunk) grid round-robin: no wave quantisation,
     // TMEM allocation / barrier setup / resident weights paid once per SM.  The CTA count is a multiple of nchunks so
     // every CTA keeps one column chunk (resident weights stay valid for its whole life).
-    static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+    const int sms = sms_dev > 0 ? sms_dev : 148;
     const long long W = (long long)ntiles * nseg * w.nchunks;
     if (W <= 0 || W > 0x7fffffffLL) return -1;
     typedef void (*Kern)(const ConvP, const TcP, const CUtensorMap);
     static const Kern kerns[10] = {conv_tc_kernel<1, 0, 0>, conv_tc_kernel<2, 0, 0>, conv_tc_kernel<3, 0, 0>, conv_tc_kernel<4, 0, 0>,
                                   conv_tc_kernel<1, 0, 1>, conv_tc_kernel<2, 0, 1>, conv_tc_kernel<3, 0, 1>, conv_tc_kernel<4, 0, 1>,
                                   conv_tc_kernel<4, 1, 0>, conv_tc_kernel<4, 1, 0, 1>};
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int i = 0; i < 10; ++i) cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    // (the dynamic shared-memory limit of these kernels is raised per device by tc_device_setup())
     const int nct = std::min(4, w.NC / 16);
     // single-unit tiles (same formulas as the kernel): column-split layers whose whole K fits one promotion unit
     bool single = false;

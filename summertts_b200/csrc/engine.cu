@@ -22,6 +22,7 @@
 #include "model.hpp"
 #ifdef STTS_WITH_TC
 #include "conv_tc.cuh"
+#include "rb_fused.cuh"
 #endif
 
 namespace stts {
@@ -56,6 +57,7 @@ struct DConv {
     double macs_row = 0;  // algorithmic MACs per input-rate row (un-expanded taps, live outputs only)
 #ifdef STTS_WITH_TC
     TcWeights tc;        // split-fp16 UMMA-layout copy (filled when the layer is tensor-path eligible)
+    RbWeights rb;        // merged split-fp16 stages for the fused ResBlock1-pair kernel (rb_fused.cuh), ResBlock1 convs only
 #endif
 };
 struct DLN {
@@ -249,7 +251,7 @@ struct stts_engine {
         pl.base = ws.get<__half>((size_t)pl.rows_p * C * 2);
         return pl;
     }
-    bool tc_layer(const DConv& c) const { return tensor_mode == 1 && c.tc.ok && (c.k - 1) * c.dil <= TC_GAP && c.padl <= TC_GAP; }
+    bool tc_layer(const DConv& c) const { return tensor_mode >= 1 && c.tc.ok && (c.k - 1) * c.dil <= TC_GAP && c.padl <= TC_GAP; }
 #endif
     template <typename T>
     T* dalloc(size_t n) {
@@ -274,7 +276,7 @@ struct stts_engine {
     // Build a dense conv in device layout [k][Cin'][CoutW'] from a file record W[o][k][c].
     // omap[new_o] = orig_o, cmap[new_c] = orig_c (identity when empty); sign scales w and b.
     DConv make_conv(const ConvRec& r, const std::vector<int>& omap = {}, const std::vector<int>& cmap = {},
-                    float sign = 1.f, int padl = -1, bool tc_ok = true) {
+                    float sign = 1.f, int padl = -1, bool tc_ok = true, bool rb_pair = false) {
         if (r.sep) throw Unsupported("depthwise record passed to dense conv builder");
         DConv d;
         d.Cout = omap.empty() ? r.outCh : (int)omap.size();
@@ -302,8 +304,9 @@ struct stts_engine {
         }
 #ifdef STTS_WITH_TC
         if (tc_ok) tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
+        if (rb_pair && d.Cin == d.Cout) rb_prepare_weights(d.rb, w.data(), d.k, d.Cin, d.CoutW, d.dil, d.padl, d.b, owned);
 #else
-        (void)tc_ok;
+        (void)tc_ok; (void)rb_pair;
 #endif
         return d;
     }
@@ -402,7 +405,7 @@ struct stts_engine {
         p.in_act = o.in_act; p.in_slope = o.in_slope; p.epi = o.epi; p.div = o.div; p.split = o.split;
         p.y2_store = o.y2_store;
 #ifdef STTS_WITH_TC
-        if (tensor_mode == 1 && o.allow_tc && tc_eligible(c.tc, p)) {
+        if (tensor_mode >= 1 && o.allow_tc && tc_eligible(c.tc, p)) {
             Planes in;
             if (o.in_planes && o.in_planes->base) in = *o.in_planes;
             else {   // the producer was not a tensor-core conv: split fp32 rows into planes here
@@ -416,7 +419,7 @@ struct stts_engine {
             if (o.out2_planes) out.y2p = *o.out2_planes;
             out.out_act = o.out_act; out.out_slope = o.out_slope; out.write_f32 = o.write_f32;
             out.y_tt = o.y_tt; out.y2_tt = o.y2_tt; out.res_tt = o.res_tt; out.acc_tt = o.acc_tt; out.acc_src = o.acc_src;
-            const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream);
+            const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream, sms);
             if (r == -2) throw std::runtime_error("tile-transposed tensor with a row stride (planning bug)");
             if (r < 0) throw CudaError("cuTensorMapEncodeTiled failed for an activation plane");
             launches += r;
@@ -471,6 +474,33 @@ struct stts_engine {
         }
     }
 
+    // Per-DEVICE one-time state (function attributes are per device/context: an engine on GPU 1 of the same process needs its
+    // own call), SM count and the overflow flag word.
+    int sms = 148;
+    unsigned int* d_flags = nullptr;
+    unsigned int* h_flags = nullptr;   // pinned
+    int64_t fallbacks = 0;       // batches re-run on the fp32 FFMA tiles because an activation left the split-fp16 range
+    void device_setup() {
+        int n = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+        if (n > 0) sms = n;
+        d_flags = dalloc<unsigned int>(4);
+        CUDA_CHECK(cudaMemset(d_flags, 0, 16));
+        CUDA_CHECK(cudaMallocHost((void**)&h_flags, 16));
+        h_flags[0] = 0;
+#ifdef STTS_WITH_TC
+        CUDA_CHECK(tc_device_setup());
+        CUDA_CHECK(rb_device_setup());
+#endif
+    }
+    void prof_begin(ProfRec& r, double flops) {
+        r.cls = curCls; r.a = prof_event(); r.b = prof_event(); r.flops = flops;
+        CUDA_CHECK(cudaEventRecord(r.a, stream));
+    }
+    void prof_end(ProfRec& r) {
+        CUDA_CHECK(cudaEventRecord(r.b, stream));
+        profRecs.push_back(r);
+    }
     void build(const Model& M);
     void stage(int B_, const int32_t* ids, const int32_t* offs, const int32_t* sids, const float* ls);
     void run();
@@ -621,8 +651,8 @@ void stts_engine::build(const Model& M) {
     }
     for (size_t i = 0; i < G.rbs.size(); ++i) {
         RB rb;
-        for (auto& c : G.rbs[i].convs1) rb.c1.push_back(make_conv(c));
-        for (auto& c : G.rbs[i].convs2) rb.c2.push_back(make_conv(c));
+        for (auto& c : G.rbs[i].convs1) rb.c1.push_back(make_conv(c, {}, {}, 1.f, -1, true, true));
+        for (auto& c : G.rbs[i].convs2) rb.c2.push_back(make_conv(c, {}, {}, 1.f, -1, true, true));
         rbs.push_back(rb);
     }
     if (decType == 0) {
@@ -665,6 +695,7 @@ void stts_engine::build(const Model& M) {
     }
     if (isMS == 1) emg = upload(M.emg, (size_t)spkNum * gin);
     CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    device_setup();
     // constant DFT tables
     float c16[16], s16[16];
     for (int i = 0; i < 16; ++i) { c16[i] = (float)std::cos(2.0 * M_PI * i / 16.0); s16[i] = (float)std::sin(2.0 * M_PI * i / 16.0); }
@@ -740,6 +771,7 @@ void stts_engine::run() {
     const Seg tseg{d_toff, 1, 0};
     const Seg bseg{d_bseg, 1, 0};
     CUDA_CHECK(cudaEventRecord(ev[0], stream));
+    if (tensor_mode >= 1) CUDA_CHECK(cudaMemsetAsync(d_flags, 0, 4, stream));
 
     // ---- token-level workspace ---------------------------------------------------------------
     size_t ffnW = 0, dpW = 0;
@@ -756,7 +788,7 @@ void stts_engine::run() {
     float* fh = ws.get<float>((size_t)Tt * ffnW);
 #ifdef STTS_WITH_TC
     Planes encFhP;
-    if (tensor_mode == 1) encFhP = arena_planes(Tt, B, (int)ffnW);
+    if (tensor_mode >= 1) encFhP = arena_planes(Tt, B, (int)ffnW);
 #endif
     float* mbuf = ws.get<float>((size_t)Tt * inter);
     float* logw = ws.get<float>((size_t)Tt);
@@ -904,7 +936,7 @@ void stts_engine::run() {
         for (size_t i = 0; i < ups.size(); ++i) {
             rr *= upRates[i];
             need += ((size_t)Ft * rr * stageC[i] * 4 + 256) * 5;                                  // xx / t1 / xa / accb / accT
-            need += 3 * (((size_t)Ft * rr + 2 * (size_t)B * 64 + 256) * stageC[i] * 4 + 256);   // planes xx / t1 / xa
+            need += 6 * (((size_t)Ft * rr + 2 * (size_t)B * 64 + 256) * stageC[i] * 4 + 256);   // planes xx / t1 / xa, or xx / 2 ping-pong / 3 branch outputs (fused pairs)
         }
         if (decType != 0) {
             const size_t fr = (size_t)Ft * R + B;
@@ -936,7 +968,7 @@ void stts_engine::run() {
     float* skip = ws.get<float>((size_t)Ft * WH);
 #ifdef STTS_WITH_TC
     Planes hP, actsP, skipP;
-    bool flowTc = tensor_mode == 1 && flowN > 0;
+    bool flowTc = tensor_mode >= 1 && flowN > 0;
     for (auto& L : flow) {
         flowTc = flowTc && tc_layer(L.pre) && tc_layer(L.post);
         for (auto& c : L.in) flowTc = flowTc && tc_layer(c);
@@ -1018,10 +1050,7 @@ void stts_engine::run() {
         rate *= upRates[s];
         const size_t rows = (size_t)Ft * rate;
         float* xx = ws.get<float>(rows * C);
-        float* t1 = ws.get<float>(rows * C);
-        float* xa = ws.get<float>(rows * C);
         float* accb = ws.get<float>(rows * C);
-        float* accT = nullptr;                   // tensor path: MRF partial sums, tile-transposed
         {   // leaky(0.1) + ConvTranspose1d (phase-expanded): Generator_MS.cpp:172-175
             ConvOpts o; o.in_act = ACT_LEAKY; o.in_slope = 0.1f;
             curCls = STTS_CLS_DEC_UP; curRowsTotal = (int64_t)Ft * rate_in;
@@ -1032,19 +1061,75 @@ void stts_engine::run() {
         const int ml = maxF * rate;
 #ifdef STTS_WITH_TC
         Planes xxP, t1P, xaP;
-        bool rbTc = tensor_mode == 1;
+        bool rbTc = tensor_mode >= 1;
         for (int j = 0; j < nRbK; ++j) {
             for (auto& c : rbs[s * nRbK + j].c1) rbTc = rbTc && tc_layer(c);
             for (auto& c : rbs[s * nRbK + j].c2) rbTc = rbTc && tc_layer(c);
         }
+        // fused ResBlock1 pairs (rb_fused.cuh): 32/64-channel stages whose every pair fits the fused kernel
+        static const int env_fused = getenv("STTS_RB_FUSED") ? atoi(getenv("STTS_RB_FUSED")) : 1;
+        bool rbFused = rbTc && env_fused && (C == 32 || C == 64) && nRbK >= 1 && nRbK <= 3;
+        for (int j = 0; j < nRbK && rbFused; ++j) {
+            const RB& rb = rbs[s * nRbK + j];
+            if (rb.c1.size() != rb.c2.size() || rb.c1.empty()) rbFused = false;
+            for (size_t q = 0; q < rb.c1.size() && rbFused; ++q)
+                rbFused = rb_pair_eligible(rb.c1[q].rb, rb.c2[q].rb) && rb_plan(C, rb.c1[q].rb, rb.c2[q].rb).smem <= 227 * 1024;
+        }
         if (rbTc) {
-            xxP = arena_planes(curRowsTotal, B, C); t1P = arena_planes(curRowsTotal, B, C); xaP = arena_planes(curRowsTotal, B, C);
-            if (nRbK > 1) accT = ws.get<float>(rows * C);
+            xxP = arena_planes(curRowsTotal, B, C);
             // leaky(0.1)(xx) once for the three ResBlock1 branches (ResBlock1.cpp:61)
             dim3 g(((size_t)(ml + 2 * TC_GAP) * (C / 8) + 255) / 256, B);
             split_planes_kernel<<<g, 256, 0, stream>>>(xx, C, sseg, C, ACT_LEAKY, 0.1f, xxP);
             launch_check();
         }
+        if (rbFused) {
+            // x (planes of leaky(x)) -> pair -> pair -> pair (planes of x') per branch; MRF mean over the branches' planes.
+            // No fp32 intermediate exists in HBM (ResBlock1.cpp:55-69, Generator_MS.cpp:177-196).
+            Planes pp[2] = {arena_planes(curRowsTotal, B, C), arena_planes(curRowsTotal, B, C)};
+            Planes op[3];
+            for (int j = 0; j < nRbK; ++j) op[j] = arena_planes(curRowsTotal, B, C);
+            for (int q = 0; q < 2 + nRbK; ++q) {
+                const Planes& z = q < 2 ? pp[q] : op[q - 2];
+                dim3 g((2 * (C / 8) * 2 * TC_GAP + 255) / 256, B);
+                planes_gap_zero_kernel<<<g, 256, 0, stream>>>(z, sseg);
+                launch_check();
+            }
+            for (int j = 0; j < nRbK; ++j) {
+                const RB& rb = rbs[s * nRbK + j];
+                const int nb = (int)rb.c1.size();
+                const Planes* in = &xxP;
+                for (int q = 0; q < nb; ++q) {
+                    const bool last = q == nb - 1;
+                    const Planes* out = last ? &op[j] : &pp[q & 1];
+                    ProfRec pr;
+                    if (profOn) prof_begin(pr, 2.0 * (rb.c1[q].macs_row + rb.c2[q].macs_row) * (double)curRowsTotal);
+                    const int r = rb_pair_launch(C, rb.c1[q].rb, rb.c2[q].rb, *in, *out, sseg, B, ml, 0.1f, last ? ACT_NONE : ACT_LEAKY, 0.1f,
+                                                 tensor_mode == 2 ? 1 : 0, sms, d_flags, stream);
+                    if (r < 0) throw CudaError("fused ResBlock1 pair launch failed (" + std::to_string(r) + ")");
+                    launch_check();
+                    if (profOn) prof_end(pr);
+                    in = out;
+                }
+            }
+            {
+                dim3 g(((size_t)ml * (C / 8) + 255) / 256, B);
+                mrf_combine_kernel<<<g, 256, 0, stream>>>(op[0], op[nRbK > 1 ? 1 : 0], op[nRbK > 2 ? 2 : 0], nRbK, (float)nRbK, sseg, accb, C, 0.f);
+                launch_check();
+            }
+            cur = accb; curC = C;
+            continue;
+        }
+        float* t1 = ws.get<float>(rows * C);
+        float* xa = ws.get<float>(rows * C);
+        float* accT = nullptr;                   // tensor path: MRF partial sums, tile-transposed
+        if (rbTc) {
+            t1P = arena_planes(curRowsTotal, B, C); xaP = arena_planes(curRowsTotal, B, C);
+            if (nRbK > 1) accT = ws.get<float>(rows * C);
+        }
+#else
+        float* t1 = ws.get<float>(rows * C);
+        float* xa = ws.get<float>(rows * C);
+        float* accT = nullptr;
 #endif
         for (int j = 0; j < nRbK; ++j) {                                         // MRF: Generator_MS.cpp:177-196
             RB& rb = rbs[s * nRbK + j];
@@ -1124,7 +1209,19 @@ void stts_engine::run() {
     pcm_kernel<<<(St + 255) / 256, 256, 0, stream>>>(o, d_pcm, (size_t)St);
     launch_check();
     CUDA_CHECK(cudaEventRecord(ev[5], stream));
+    if (tensor_mode >= 1) CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, 4, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (tensor_mode >= 1 && (h_flags[0] & 1u)) {
+        // an activation left the range the split-fp16 operands can represent (|x| > ~8000; shipped models peak at 126):
+        // the saturated result is discarded and the batch is recomputed on the fp32 FFMA tiles
+        const int keep = tensor_mode;
+        h_flags[0] = 0;
+        ++fallbacks;
+        tensor_mode = 0;
+        try { run(); } catch (...) { tensor_mode = keep; throw; }
+        tensor_mode = keep;
+        return;
+    }
     for (int i = 0; i < 5; ++i) CUDA_CHECK(cudaEventElapsedTime(&lastMs[i], ev[i], ev[i + 1]));
     CUDA_CHECK(cudaEventElapsedTime(&lastMs[5], ev[0], ev[5]));
     if (profOn) prof_collect();
@@ -1214,6 +1311,7 @@ void stts_destroy(stts_engine* e) {
         if (p) cudaFree(p);
     if (e->hostPcm) cudaFreeHost(e->hostPcm);
     if (e->hostInts) cudaFreeHost(e->hostInts);
+    if (e->h_flags) cudaFreeHost(e->h_flags);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->profPool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1228,6 +1326,7 @@ int32_t stts_header_field(const stts_engine* e, int32_t which) {
     return -1;
 }
 int64_t stts_kernel_launches(const stts_engine* e) { return e ? e->launches : 0; }
+int64_t stts_tensor_fallbacks(const stts_engine* e) { return e ? e->fallbacks : 0; }
 void* stts_stream(const stts_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int stts_set_tensor_path(stts_engine* e, int32_t mode) {
@@ -1396,6 +1495,7 @@ int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_float
         e = new stts_engine();
         e->device = device;
         CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->device_setup();
         Cursor c{rec, rec_floats};
         ConvRec r = transposed ? parse_convT(c) : parse_conv(c);
         if (pad_override >= 0) r.pad = pad_override;
@@ -1433,6 +1533,67 @@ int stts_test_conv1d(int device, int use_tc, const float* rec, int64_t rec_float
         *y = (float*)malloc((size_t)outRows * outC * 4);
         CUDA_CHECK(cudaMemcpy(*y, dy, (size_t)outRows * outC * 4, cudaMemcpyDeviceToHost));
         *rows = outRows; *cols = outC;
+    });
+    if (e) stts_destroy(e);
+    return rc;
+}
+
+// Op-level test hook of the fused ResBlock1 pair (rb_fused.cuh): x' = act(x + conv2(leaky(conv1(leaky(x))))) on caller data,
+// through planes in / planes out exactly as the decoder uses it.  mode 0 accurate, 1 throughput.
+int stts_test_rbpair(int device, int mode, const float* rec1, int64_t n1, const float* rec2, int64_t n2, int dil1, const float* x,
+                     int T, int nseg, const int* seg_off, int out_leaky, float** y, uint32_t* flags_out) {
+    stts_engine* e = nullptr;
+    int rc = guard([&] {
+#ifdef STTS_WITH_TC
+        if (!rec1 || !rec2 || !x || !y) throw ArgError("null argument");
+        CUDA_CHECK(cudaSetDevice(device));
+        e = new stts_engine();
+        e->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->device_setup();
+        Cursor c1{rec1, n1}, c2{rec2, n2};
+        ConvRec r1 = parse_conv(c1), r2 = parse_conv(c2);
+        if (dil1 > 0) { r1.dil = dil1; r1.pad = dil1 * (r1.k - 1) / 2; }
+        e->tc_usteps = 8;
+        DConv d1 = e->make_conv(r1, {}, {}, 1.f, -1, true, true), d2 = e->make_conv(r2, {}, {}, 1.f, -1, true, true);
+        const int C = r1.inCh;
+        if (!rb_pair_eligible(d1.rb, d2.rb)) throw Unsupported("pair is not eligible for the fused kernel");
+        std::vector<int> so;
+        if (seg_off) so.assign(seg_off, seg_off + nseg + 1); else { nseg = 1; so = {0, T}; }
+        int maxlen = 0;
+        for (int i = 0; i < nseg; ++i) maxlen = std::max(maxlen, so[i + 1] - so[i]);
+        int* dso = e->dalloc<int>(so.size());
+        CUDA_CHECK(cudaMemcpy(dso, so.data(), so.size() * 4, cudaMemcpyHostToDevice));
+        float* dx = e->upload(x, (size_t)T * C);
+        float* dy = e->dalloc<float>((size_t)T * C);
+        CUDA_CHECK(cudaMemset(dy, 0, (size_t)T * C * 4));
+        e->ensure_ws(3 * stts_engine::planes_bytes(T, nseg, C) + (1 << 20));
+        e->ws.reset();
+        const Seg seg{dso, 1, 0};
+        Planes inP = e->arena_planes(T, nseg, C), outP = e->arena_planes(T, nseg, C);
+        CUDA_CHECK(cudaMemsetAsync(outP.base, 0xff, (size_t)outP.rows_p * C * 4, e->stream));    // poison: every live row must be written
+        {
+            dim3 g(((size_t)(maxlen + 2 * TC_GAP) * (C / 8) + 255) / 256, nseg);
+            split_planes_kernel<<<g, 256, 0, e->stream>>>(dx, C, seg, C, ACT_LEAKY, 0.1f, inP);
+            dim3 g2((2 * (C / 8) * 2 * TC_GAP + 255) / 256, nseg);
+            planes_gap_zero_kernel<<<g2, 256, 0, e->stream>>>(outP, seg);
+        }
+        const int r = rb_pair_launch(C, d1.rb, d2.rb, inP, outP, seg, nseg, maxlen, 0.1f, out_leaky ? ACT_LEAKY : ACT_NONE, 0.1f, mode, e->sms,
+                                     e->d_flags, e->stream);
+        if (r < 0) throw CudaError("fused pair launch failed (" + std::to_string(r) + ")");
+        e->launch_check();
+        {
+            dim3 g(((size_t)maxlen * (C / 8) + 255) / 256, nseg);
+            mrf_combine_kernel<<<g, 256, 0, e->stream>>>(outP, outP, outP, 1, 1.f, seg, dy, C, 0.f);   // y = act(x') exactly as stored
+        }
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        e->launch_check();
+        *y = (float*)malloc((size_t)T * C * 4);
+        CUDA_CHECK(cudaMemcpy(*y, dy, (size_t)T * C * 4, cudaMemcpyDeviceToHost));
+        if (flags_out) CUDA_CHECK(cudaMemcpy(flags_out, e->d_flags, 4, cudaMemcpyDeviceToHost));
+#else
+        throw Unsupported("built without the tensor-core path");
+#endif
     });
     if (e) stts_destroy(e);
     return rc;

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
-    "stts_test_conv1d", "stts_debug_pack_weights",
+    "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks",
 ]
 
 _lib = None
@@ -74,6 +74,8 @@ def load_library():
     L.stts_debug_pack_weights.argtypes = [vp, i32, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(i64)]
     L.stts_kernel_launches.argtypes = [vp]
     L.stts_kernel_launches.restype = i64
+    L.stts_tensor_fallbacks.argtypes = [vp]
+    L.stts_tensor_fallbacks.restype = i64
     L.stts_stream.argtypes = [vp]
     L.stts_stream.restype = vp
     L.stts_set_tensor_path.argtypes = [vp, i32]
@@ -223,6 +225,10 @@ class SynthesizerTrn:
     def kernel_launches(self) -> int:
         return int(self._L.stts_kernel_launches(self._h))
 
+    def tensor_fallbacks(self) -> int:
+        """Batches recomputed on the fp32 FFMA tiles because an activation left the split-fp16 range."""
+        return int(self._L.stts_tensor_fallbacks(self._h))
+
     def stream(self) -> int:
         return int(self._L.stts_stream(self._h) or 0)
 
@@ -257,6 +263,24 @@ def test_conv1d(rec, x, use_tc=0, transposed=False, stride=1, pad=-1, dil=0, seg
     out = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_float)), shape=(n,)).copy().reshape(r.value, c.value)
     L.stts_free(y)
     return out
+
+
+def test_rbpair(rec1, rec2, x, dil1=1, mode=0, seg_off=None, out_leaky=True, device=0):
+    """Op-level hook: one fused ResBlock1 pair (rb_fused.cuh) on x[T][C]; returns (y, flags)."""
+    L = load_library()
+    L.stts_test_rbpair.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    rec1 = np.ascontiguousarray(rec1, dtype=np.float32)
+    rec2 = np.ascontiguousarray(rec2, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    so = None if seg_off is None else np.ascontiguousarray(seg_off, dtype=np.int32)
+    y, fl = C.c_void_p(), C.c_uint32(0)
+    _check(L.stts_test_rbpair(device, int(mode), rec1.ctypes.data, rec1.size, rec2.ctypes.data, rec2.size, int(dil1), x.ctypes.data,
+                              x.shape[0], 0 if so is None else so.size - 1, None if so is None else so.ctypes.data,
+                              1 if out_leaky else 0, C.byref(y), C.byref(fl)))
+    out = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_float)), shape=(x.size,)).copy().reshape(x.shape)
+    L.stts_free(y)
+    return out, int(fl.value)
 
 
 def debug_pack_weights(w, usteps=0):
