@@ -493,6 +493,18 @@ struct stts_engine {
         CUDA_CHECK(rb_device_setup());
 #endif
     }
+#ifdef STTS_WITH_TC
+    // Super-tile table of the fused ResBlock1-pair kernel for one segmentation (lens = host copy of the row counts) and
+    // tile height ov: built on the device from the same offsets, size computed here.
+    const int2* rb_tiles(const Seg& seg, const std::vector<int>& lens, int ov, int& ntiles) {
+        ntiles = 0;
+        for (int L : lens) ntiles += (L + ov - 1) / ov;
+        int2* t = ws.get<int2>((size_t)std::max(ntiles, 1));
+        rb_tiles_kernel<<<1, 256, 0, stream>>>(seg, (int)lens.size(), ov, t, ntiles);
+        launch_check();
+        return t;
+    }
+#endif
     void prof_begin(ProfRec& r, double flops) {
         r.cls = curCls; r.a = prof_event(); r.b = prof_event(); r.flops = flops;
         CUDA_CHECK(cudaEventRecord(r.a, stream));
@@ -925,7 +937,7 @@ void stts_engine::run() {
     for (int r : upRates) R *= r;
     const int tailMul = decType == 0 ? 1 : (decType == 2 ? 4 : 16);
     St = (int64_t)Ft * R * tailMul;
-    size_t need = tokEnd + 4096;
+    size_t need = tokEnd + 4096 + (size_t)(1 << 20);   // (+ super-tile tables of the fused ResBlock1 pairs)
     const int WH = wnHidden;
     need += ((size_t)Ft * (inter * 2 + WH * 3)) * 4 + 8 * 256;
     need += 3 * ((size_t)Ft + 2 * (size_t)B * 64 + 256) * WH * 4 + 4096;   // split-fp16 planes of h / acts / skip
@@ -1094,16 +1106,20 @@ void stts_engine::run() {
                 planes_gap_zero_kernel<<<g, 256, 0, stream>>>(z, sseg);
                 launch_check();
             }
+            std::vector<int> lens(B);
+            for (int u = 0; u < B; ++u) lens[u] = (h_foff[u + 1] - h_foff[u]) * rate;
             for (int j = 0; j < nRbK; ++j) {
                 const RB& rb = rbs[s * nRbK + j];
                 const int nb = (int)rb.c1.size();
                 const Planes* in = &xxP;
+                const int2* tiles = nullptr; int ntiles = 0, tiles_ov = 0;
                 for (int q = 0; q < nb; ++q) {
                     const bool last = q == nb - 1;
                     const Planes* out = last ? &op[j] : &pp[q & 1];
+                    if (rb_ov(rb.c2[q].rb) != tiles_ov) { tiles_ov = rb_ov(rb.c2[q].rb); tiles = rb_tiles(sseg, lens, tiles_ov, ntiles); }
                     ProfRec pr;
                     if (profOn) prof_begin(pr, 2.0 * (rb.c1[q].macs_row + rb.c2[q].macs_row) * (double)curRowsTotal);
-                    const int r = rb_pair_launch(C, rb.c1[q].rb, rb.c2[q].rb, *in, *out, sseg, B, ml, 0.1f, last ? ACT_NONE : ACT_LEAKY, 0.1f,
+                    const int r = rb_pair_launch(C, rb.c1[q].rb, rb.c2[q].rb, *in, *out, sseg, tiles, ntiles, 0.1f, last ? ACT_NONE : ACT_LEAKY, 0.1f,
                                                  tensor_mode == 2 ? 1 : 0, sms, d_flags, stream);
                     if (r < 0) throw CudaError("fused ResBlock1 pair launch failed (" + std::to_string(r) + ")");
                     launch_check();
@@ -1567,7 +1583,7 @@ int stts_test_rbpair(int device, int mode, const float* rec1, int64_t n1, const 
         float* dx = e->upload(x, (size_t)T * C);
         float* dy = e->dalloc<float>((size_t)T * C);
         CUDA_CHECK(cudaMemset(dy, 0, (size_t)T * C * 4));
-        e->ensure_ws(3 * stts_engine::planes_bytes(T, nseg, C) + (1 << 20));
+        e->ensure_ws(3 * stts_engine::planes_bytes(T, nseg, C) + (size_t)T / 16 + (2 << 20));
         e->ws.reset();
         const Seg seg{dso, 1, 0};
         Planes inP = e->arena_planes(T, nseg, C), outP = e->arena_planes(T, nseg, C);
@@ -1578,7 +1594,11 @@ int stts_test_rbpair(int device, int mode, const float* rec1, int64_t n1, const 
             dim3 g2((2 * (C / 8) * 2 * TC_GAP + 255) / 256, nseg);
             planes_gap_zero_kernel<<<g2, 256, 0, e->stream>>>(outP, seg);
         }
-        const int r = rb_pair_launch(C, d1.rb, d2.rb, inP, outP, seg, nseg, maxlen, 0.1f, out_leaky ? ACT_LEAKY : ACT_NONE, 0.1f, mode, e->sms,
+        std::vector<int> lens(nseg);
+        for (int i = 0; i < nseg; ++i) lens[i] = so[i + 1] - so[i];
+        int ntiles = 0;
+        const int2* tiles = e->rb_tiles(seg, lens, rb_ov(d2.rb), ntiles);
+        const int r = rb_pair_launch(C, d1.rb, d2.rb, inP, outP, seg, tiles, ntiles, 0.1f, out_leaky ? ACT_LEAKY : ACT_NONE, 0.1f, mode, e->sms,
                                      e->d_flags, e->stream);
         if (r < 0) throw CudaError("fused pair launch failed (" + std::to_string(r) + ")");
         e->launch_check();

@@ -28,7 +28,7 @@
 
 namespace stts {
 
-constexpr int RB_THREADS = 384;     // warps 0-3 / 4-7: epilogue sets of M-tile 0 / 1; 8, 9: MMA issuers; 10: x-tile TMA; 11: weights
+constexpr int RB_THREADS = 672;     // warps 0-15: four epilogue sets (M-tile x column half); 16-19: MMA issuers (kind x M-tile); 20: producer (x tiles + weights)
 constexpr int RB_MAX_STAGES = 32;   // weight stages (taps of conv1 + conv2) when resident; ring depth otherwise
 
 struct RbWeights {                  // one conv of the pair, merged split-fp16 stages [tap][C/8][hi rows C | lo rows C][8]
@@ -41,7 +41,9 @@ struct RbWeights {                  // one conv of the pair, merged split-fp16 s
 
 struct RbP {
     Seg seg;
-    int gx, work_items;              // super-tiles of the longest utterance; gx * utterances
+    const int2* tiles;               // [work_items] (utterance, first row) of every super-tile, built by rb_tiles_kernel
+    int work_items;                  // number of super-tiles: a kernel PARAMETER, so every role's tile loop has uniform bounds
+                                     // (the MMA issuers keep their descriptors in uniform registers only in provably uniform loops)
     const __half* w1; const __half* w2;
     const float* b1; const float* b2;
     float isc1, isc2;
@@ -56,6 +58,7 @@ struct RbP {
     int tmem_cols;
     Planes outp;                     // destination planes (written with 1-D bulk stores of the exact valid rows)
     unsigned int* flags;             // bit 0: an activation exceeded the fp16 range of the split (|8 x| > 65504)
+    int dbg;                         // experiments (STTS_RB_DBG): bit 0 = epilogue / producer mbarrier polls back off with nanosleep
     long long* trace;                // optional clock64 timeline of CTA 0 (STTS_TC_TRACE_BUILD + STTS_RB_TRACE): [6 roles][1024]
 };
 
@@ -69,36 +72,221 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // lane 0 polls, the warp re-converges, then every lane observes the (already complete) phase itself
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* b, uint32_t parity, unsigned ns) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (!done) __nanosleep(ns);
+    }
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* b, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait_all(uint64_t* b, uint32_t parity) {
-    mbar_wait_warp(b, parity);
+    if ((threadIdx.x & 31) == 0) mbar_wait(b, parity);
+    __syncwarp();
     mbar_wait(b, parity);
 }
 
-struct RbTile { int w, W, step, gx; int u, x, seg0, len, t0; long long prow_u; };
-__device__ __forceinline__ bool rb_next(RbTile& it, const Seg& seg, int ov) {
-    while (it.w < it.W) {
-        const int w = it.w;
-        it.w += it.step;
-        const int u = w / it.gx, x = w - u * it.gx;
-        const int len = seg_len(seg, u);
-        if (x * ov >= len) continue;
-        it.u = u; it.x = x; it.len = len; it.t0 = x * ov;
-        it.seg0 = seg_start(seg, u);
-        it.prow_u = planes_row(seg, u);
-        return true;
+struct RbTile { int u, seg0, len, t0; long long prow_u; };
+__device__ __forceinline__ RbTile rb_tile(const RbP& p, int w) {
+    RbTile it;
+    const int2 e = __ldg(p.tiles + w);
+    it.u = e.x; it.t0 = e.y;
+    it.len = seg_len(p.seg, e.x);
+    it.seg0 = seg_start(p.seg, e.x);
+    it.prow_u = planes_row(p.seg, e.x);
+    return it;
+}
+// (utterance, first row) of every super-tile of `ov` rows, utterance-major; one block
+__global__ void __launch_bounds__(256) rb_tiles_kernel(Seg seg, int nseg, int ov, int2* __restrict__ out, int cap) {
+    __shared__ int scan[256];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int u0 = 0; u0 < nseg; u0 += 256) {
+        const int u = u0 + threadIdx.x;
+        const int n = u < nseg ? (seg_len(seg, u) + ov - 1) / ov : 0;
+        scan[threadIdx.x] = n;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int v = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int first = base + scan[threadIdx.x] - n;
+        for (int x = 0; x < n; ++x)
+            if (first + x < cap) out[first + x] = make_int2(u, x * ov);
+        __syncthreads();
+        if (threadIdx.x == 255) base += scan[255];
+        __syncthreads();
     }
-    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MMA issuer (one warp per ROLE).  Everything that feeds a tcgen05.mma operand is derived from kernel parameters,
+// blockIdx and loop counters with parameter bounds only, and ROLE is a template constant: ptxas then keeps the descriptors
+// in uniform registers (a data-dependent tile loop cost ~14 R2UR moves and 250-300 cycles per MMA here).
+//   mode 0: ROLE 0 issues A_hi x [W_hi | W_lo] (N = 2C) into main[mt], ROLE 1 issues A_lo x W_hi (N = C) into corr[mt];
+//   mode 1: ROLE r issues A_hi x W_hi (N = C) for M-tile r.
+// ---------------------------------------------------------------------------------------------
+template <int C, int KIND>
+__device__ __forceinline__ void rb_issuer(const RbP& p, const int mt, const uint32_t abuf_s, const uint32_t t1_s, const uint32_t w_s, const uint32_t tmem,
+                                          uint64_t* a_full, uint64_t* m_full, uint64_t* m_empty, uint64_t* c_full, uint64_t* c_empty,
+                                          uint64_t* t1_full, uint64_t* b_full, uint64_t* b_empty, long long* rtr) {
+    // ONE thread per (KIND, M-tile) runs a whole issue loop: four issuing threads per CTA.  A single thread sustains one
+    // MMA per ~100 cycles in this loop (R2UR moves + the per-instruction election wrapper ptxas emits in divergent code),
+    // the tensor pipe retires a small-N MMA in 40-65 cycles, so four streams keep it busy and hide each other's waits.
+    //   mode 0: KIND 0 = A_hi x [W_hi | W_lo] (N = 2C) into main[mt] in promotion units, KIND 1 = A_lo x W_hi (N = C) into corr[mt];
+    //   mode 1: KIND 0 = even taps, KIND 1 = odd taps of A_hi x W_hi (N = C), into main[mt] / corr[mt] (summed by the epilogue).
+    constexpr int G = C / 8, KS = C / 16;
+    const int mode = p.mode;
+    const uint32_t a_tile = (uint32_t)C * p.xr1 * 4;
+    const uint32_t stage16 = (uint32_t)(4 * C * C) >> 4;                 // weight stage in 16-byte units
+    const int UPT = mode ? 64 : max(1, p.usteps / KS);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(((mode || KIND == 1) ? C : 2 * C) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t b_lbo = 2 * C * 16;        // bytes between the two 8-channel groups of a K-step (merged stage: 2C rows)
+    constexpr uint32_t b_k16 = (2 * b_lbo) >> 4;
+    const uint64_t b_desc0 = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46) | (uint64_t)((w_s & 0x3FFFFu) >> 4);
+    uint32_t af_par0 = 0, af_par1 = 0, t1_par = 0, e_par = 1;
+    int bs = 0; uint32_t bph = 0;                 // ring slot / phase
+    const int W = p.work_items, step = gridDim.x;
+    const uint32_t d_t = tmem + (uint32_t)(mt * 3 * C) + (KIND == 1 ? 2 * C : 0);
+    uint64_t* full_bar = KIND == 0 ? &m_full[mt] : &c_full[mt];
+    uint64_t* empty_bar = KIND == 0 ? &m_empty[mt] : &c_empty[mt];
+    const int tstep = mode ? 2 : 1, toff = mode ? KIND : 0;     // mode 1: this issuer's taps are toff, toff + 2, ...
+    int tile = 0;
+#ifdef STTS_TC_TRACE_BUILD
+    int fine = 0;
+#endif
+    for (int w = blockIdx.x; w < W; w += step, ++tile) {
+        const int buf = p.abufs == 2 ? (tile & 1) : 0;
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+            const int k = ph ? p.k2 : p.k1;
+            const uint32_t dil = ph ? 1u : (uint32_t)p.d1;
+            const int XR = ph ? p.xr2 : p.xr1;
+            RB_TS(KIND, tile * 8 + ph * 3);
+            if (ph == 0) {
+                if (buf) { mbar_wait(&a_full[1], af_par1); af_par1 ^= 1; } else { mbar_wait(&a_full[0], af_par0); af_par0 ^= 1; }
+            } else { mbar_wait(t1_full, t1_par); t1_par ^= 1; }
+            tc_fence_after();
+            RB_TS(KIND, tile * 8 + ph * 3 + 1);
+            const uint32_t a_lbo = (uint32_t)XR * 16;
+            const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+            const uint32_t a_k16 = (2 * a_lbo) >> 4;
+            const uint32_t a_plane = (mode == 0 && KIND == 1) ? (uint32_t)G * a_lbo : 0u;      // mode 0 corr reads the lo plane
+            const uint32_t a_s = (ph ? t1_s + (uint32_t)(mt * 128) * 16 : abuf_s + (uint32_t)(buf * 2 + mt) * a_tile) + a_plane;
+            const int NU = (mode || KIND == 1) ? 1 : (k + UPT - 1) / UPT;       // promotion units (main accumulator of mode 0 only)
+            const int sbase = (p.resident && ph) ? p.k1 : 0;
+#pragma unroll 1
+            for (int un = 0; un < NU; ++un) {
+                const int tap0 = (NU == 1 ? 0 : un * UPT) + toff, tap1 = NU == 1 ? k : min(k, un * UPT + UPT);
+                mbar_wait(empty_bar, e_par); e_par ^= 1;          // accumulator drained by the epilogue sets
+                tc_fence_after();
+                uint64_t da = a_bits | (uint64_t)(((a_s + (uint32_t)tap0 * dil * 16) & 0x3FFFFu) >> 4);
+                uint32_t acc = 0u;
+#ifdef STTS_TC_TRACE_BUILD
+                if (tile == 1 && mt == 0 && fine < 250) { RB_TS(4 + KIND, fine * 2); }
+#endif
+                if (p.resident) {
+                    if (tile == 0) {
+                        for (int tap = tap0; tap < tap1; tap += tstep) mbar_wait(&b_full[sbase + tap], 0);
+                        tc_fence_after();
+                    }
+                    uint64_t db = b_desc0 + (uint32_t)(sbase + tap0) * stage16;
+#pragma unroll 1
+                    for (int tap = tap0; tap < tap1; tap += tstep) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) tc_mma_f16(d_t, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc, ks == 0 ? acc : 1u);
+                        acc = 1u;
+                        da += dil * (uint32_t)tstep; db += stage16 * (uint32_t)tstep;
+                    }
+                } else {
+                    // ring: every issuer walks all the slots of the unit, waits / issues / frees only at its own taps
+                    const int r0 = NU == 1 ? 0 : un * UPT;
+#pragma unroll 1
+                    for (int tap = r0; tap < tap1; ++tap) {
+                        const int s = bs;
+                        const uint32_t sph = bph;
+                        if (++bs == p.nb) { bs = 0; bph ^= 1; }
+                        if (mode && ((tap - toff) & 1)) continue;
+                        mbar_wait(&b_full[s], sph);
+                        tc_fence_after();
+                        const uint64_t db = b_desc0 + (uint32_t)s * stage16;
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) tc_mma_f16(d_t, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc, ks == 0 ? acc : 1u);
+                        acc = 1u;
+                        da += dil * (uint32_t)tstep;
+                        tc_commit(&b_empty[s]);
+                    }
+                }
+                tc_commit(full_bar);
+#ifdef STTS_TC_TRACE_BUILD
+                if (tile == 1 && mt == 0 && fine < 250) { RB_TS(4 + KIND, fine * 2 + 1); ++fine; }
+#endif
+            }
+            RB_TS(KIND, tile * 8 + ph * 3 + 2);
+        }
+    }
+}
+
+// 16-column / 32-column TMEM loads without the wait (several in flight, one tcgen05.wait::ld)
+template <int CH>
+__device__ __forceinline__ void tc_ld_nowait(uint32_t taddr, uint32_t* r) {
+    if constexpr (CH == 32) tc_ld32_nowait(taddr, r);
+    else
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+}
+// 8 values already in the x8 domain -> hi | lo fp16 planes (two packed conversions per pair; saturating)
+__device__ __forceinline__ uint32_t cvt_h2_sat(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ void split8_scaled(const float* v, uint4& hi, uint4& lo) {
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hh[i] = cvt_h2_sat(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+        ll[i] = cvt_h2_sat(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    }
+    hi = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    lo = make_uint4(ll[0], ll[1], ll[2], ll[3]);
 }
 
 template <int C>
 __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, const __grid_constant__ CUtensorMap imap) {
     constexpr int G = C / 8;          // 16-byte channel groups per plane
     constexpr int KS = C / 16;        // K = 16 MMA steps per tap
+    constexpr int CH = C / 2;         // columns per epilogue thread (a row is shared by two threads of different warps)
+    constexpr int GH = G / 2;         // channel groups per epilogue thread
     extern __shared__ __align__(128) uint8_t rsm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a warp reduction (REDUX writes a uniform register: the role branches below are warp-uniform)
+    const int warp = __reduce_max_sync(0xffffffffu, tid >> 5);
     const int XR1 = p.xr1, XR2 = p.xr2, OV = p.ov;
     const uint32_t a_tile = (uint32_t)C * XR1 * 4;           // bytes of one M-tile's x planes: [2G][XR1][16 B]
     const uint32_t t1_bytes = (uint32_t)C * XR2 * 4;         // [2G][XR2][16 B]   (aliased by the output tile [2G][OV][16 B])
@@ -117,23 +305,21 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     uint64_t* b_full = bars + 13;        // [RB_MAX_STAGES]
     uint64_t* b_empty = b_full + RB_MAX_STAGES;   // [RB_MAX_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + RB_MAX_STAGES);
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [2][C]
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [2][C], x8 domain
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2);
-            mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 128);
-            mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 128);
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 4);      // one arrival per epilogue set (M-tile, column half)
+            mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 8);      // one arrival per warp of the M-tile's two sets
+            mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 8);
         }
-        mbar_init(t1_full, 256);
-        for (int s = 0; s < RB_MAX_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }
+        mbar_init(t1_full, 16);                                        // one arrival per epilogue warp
+        for (int s = 0; s < RB_MAX_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], p.mode ? 2 : 4); }   // issuers that read a stage
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 2 * C) sbias[tid] = tid < C ? (p.b1 ? __ldg(p.b1 + tid) : 0.f) : (p.b2 ? __ldg(p.b2 + tid - C) : 0.f);
-    // rows >= 256 of T1 are never produced by conv1; they only feed output rows >= OV, which are discarded, but must not
-    // hold NaN patterns that a later kernel version might read: zero the whole buffer once
+    if (tid < 2 * C) sbias[tid] = TC_ASCALE * (tid < C ? (p.b1 ? __ldg(p.b1 + tid) : 0.f) : (p.b2 ? __ldg(p.b2 + tid - C) : 0.f));
     for (uint32_t i = tid; i < t1_bytes / 16; i += RB_THREADS) reinterpret_cast<uint4*>(t1)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 8) {
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -141,22 +327,29 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;      // M-tile mt: main @ mt*3C (2C columns), corr @ mt*3C + 2C (C columns)
+    const uint32_t tmem = *tmem_slot;      // M-tile mt: main @ mt*3C (2C columns: hi*hi | hi*lo), corr @ mt*3C + 2C (C columns)
 
-    RbTile it;
-    it.w = blockIdx.x; it.W = p.work_items; it.step = gridDim.x; it.gx = p.gx;
-    long long* rtr = (p.trace && blockIdx.x == 0 && (threadIdx.x & 127) == 0) ? p.trace : nullptr;   // tid 0, 128 (sets), 256 (issuer 0), ... see roles below
+    const int W = p.work_items, wstep = gridDim.x;
+    long long* rtr = nullptr;
     const int UPT = p.mode ? 64 : max(1, p.usteps / KS);     // taps per promotion unit
 
-    if (warp < 8) {
-        // ================= promotion + epilogues of M-tile `mt` ======================================
-        const int mt = warp >> 2, wq = warp & 3, tl = tid & 127;
-        const uint32_t tmain = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * 3 * C);
+    if (warp < 16) {
+        // ================= promotion + epilogues: set (M-tile mt, column half hf), one row x CH columns per thread ==========
+        const int wq = warp & 3, mt = (warp >> 2) & 1, hf = warp >> 3;
+        const int tl = wq * 32 + lane;                 // TMEM lane = row inside the M-tile
+        const int c0 = hf * CH, g0 = hf * GH;
+        const uint32_t tmain = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * 3 * C + c0);
         const uint32_t tcorr = tmain + 2 * C;
+        if (p.trace && blockIdx.x == 0 && tl == 0 && hf == 0) rtr = p.trace;
         uint32_t mf_par = 0, cf_par = 0;
-        bool ovf = false;
-        float racc[C];
-        for (int tile = 0; rb_next(it, p.seg, OV); ++tile) {
+        float amax = 0.f;                               // largest |8 x| converted (overflow check of the saturating split)
+        float racc[CH];
+        const float isc1 = p.isc1 * TC_ASCALE, isc2 = p.isc2 * TC_ASCALE;
+        const float rinv = p.in_slope != 0.f ? 1.0f / p.in_slope : 1.0f;              // unleaky(s) = min(s, s * rinv)
+        const float oslope = p.out_act == ACT_LEAKY ? p.out_slope : 1.0f;              // leaky(y) = max(y, y * slope)
+        int tile = 0;
+        for (int w = blockIdx.x; w < W; w += wstep, ++tile) {
+            const RbTile it = rb_tile(p, w);
             const int buf = p.abufs == 2 ? (tile & 1) : 0;
             for (int ph = 0; ph < 2; ++ph) {
                 const int k = ph ? p.k2 : p.k1;
@@ -165,119 +358,118 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                     mbar_wait_all(&m_full[mt], mf_par); mf_par ^= 1;
                     tc_fence_after();
                     if (un == 0) RB_TS(2 + mt, tile * 8 + ph * 3);
-                    if (p.mode) {
 #pragma unroll
-                        for (int cb = 0; cb < C; cb += 16) tc_ld16(tmain + cb, racc + cb);
-                    } else {
+                    for (int cb = 0; cb < CH; cb += 16) {      // two tcgen05.ld in flight per 16-column chunk, one wait
+                        uint32_t v[16], x2[16];
+                        tc_ld_nowait<16>(tmain + cb, v);
+                        if (!p.mode) tc_ld_nowait<16>(tmain + C + cb, x2);
+                        tc_ld_wait();
+                        if (p.mode) {
 #pragma unroll
-                        for (int cb = 0; cb < C; cb += 16) {
-                            float v[16], x2[16];
-                            tc_ld16(tmain + cb, v);
-                            tc_ld16(tmain + C + cb, x2);
-                            if (un == 0) {
+                            for (int j = 0; j < 16; ++j) racc[cb + j] = __uint_as_float(v[j]);
+                        } else if (un == 0) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) racc[cb + j] = v[j] + x2[j];
-                            } else {
+                            for (int j = 0; j < 16; ++j) racc[cb + j] = __uint_as_float(v[j]) + __uint_as_float(x2[j]);
+                        } else {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) racc[cb + j] += v[j] + x2[j];
-                            }
+                            for (int j = 0; j < 16; ++j) racc[cb + j] += __uint_as_float(v[j]) + __uint_as_float(x2[j]);
                         }
                     }
                     tc_fence_before();
-                    mbar_arrive(&m_empty[mt]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&m_empty[mt]);
                 }
-                if (!p.mode) {
+                {
                     mbar_wait_all(&c_full[mt], cf_par); cf_par ^= 1;
                     tc_fence_after();
 #pragma unroll
-                    for (int cb = 0; cb < C; cb += 16) {
-                        float v[16];
-                        tc_ld16(tcorr + cb, v);
+                    for (int cb = 0; cb < CH; cb += 16) {
+                        uint32_t v[16];
+                        tc_ld_nowait<16>(tcorr + cb, v);
+                        tc_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
+                        for (int j = 0; j < 16; ++j) racc[cb + j] += __uint_as_float(v[j]);
                     }
                     tc_fence_before();
-                    mbar_arrive(&c_empty[mt]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&c_empty[mt]);
                 }
                 RB_TS(2 + mt, tile * 8 + ph * 3 + 1);
-                const int i = mt * 128 + tl;          // row of the super-tile this thread owns (TMEM lane tl of M-tile mt)
+                const int i = mt * 128 + tl;          // row of the super-tile this thread works on
                 if (ph == 0) {
                     // ---- epilogue 1: t1 = leaky(conv1 + b1), zero outside the utterance, as split-fp16 planes in smem ----
-                    if (tile > 0) {                    // the previous tile's output tile aliases T1: its TMA store must have read it
+                    if (tile > 0) {                    // the previous tile's output tile aliases T1: its bulk stores must have read it
                         if (tid < 2 * G) bulk_wait_read0();
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        asm volatile("bar.sync 1, 512;" ::: "memory");
                     }
                     const int tr = it.t0 - p.pad2 + i;
                     const bool valid = tr >= 0 && tr < it.len;
-                    const float isc = p.isc1;
                     uint8_t* dst = t1 + (size_t)i * 16;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
+                    for (int gg = 0; gg < GH; ++gg) {
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float y = fmaf(racc[8 * g + j], isc, sbias[8 * g + j]);
-                            y = y < 0.f ? y * 0.1f : y;
-                            ovf |= valid && fabsf(y) > 8000.f;
-                            v[j] = valid ? y : 0.f;
+                            float y = fmaf(racc[8 * gg + j], isc1, sbias[c0 + 8 * gg + j]);
+                            y = fmaxf(y, y * 0.1f);
+                            amax = fmaxf(amax, valid ? fabsf(y) : 0.f);
+                            v[j] = y;
                         }
                         uint4 hi, lo;
-                        split8(v, hi, lo);
-                        *reinterpret_cast<uint4*>(dst + (size_t)g * XR2 * 16) = hi;
-                        if (!p.mode) *reinterpret_cast<uint4*>(dst + (size_t)(G + g) * XR2 * 16) = lo;
+                        split8_scaled(v, hi, lo);
+                        if (!valid) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
+                        *reinterpret_cast<uint4*>(dst + (size_t)(g0 + gg) * XR2 * 16) = hi;
+                        if (!p.mode) *reinterpret_cast<uint4*>(dst + (size_t)(G + g0 + gg) * XR2 * 16) = lo;
                     }
                     fence_proxy_async();
-                    mbar_arrive(t1_full);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t1_full);
                     RB_TS(2 + mt, tile * 8 + 2);
                 } else {
-                    // ---- epilogue 2: x' = act(conv2 + b2 + x), x from the x tile in smem; -> output tile -> TMA store ----
+                    // ---- epilogue 2: x' = act(conv2 + b2 + x), x from the x tile in smem; -> output tile -> bulk stores ----
                     const int tr = it.t0 + i;
                     const bool valid = i < OV && tr < it.len;
-                    const float isc = p.isc2;
                     const uint8_t* xs = abuf + (size_t)(buf * 2 + mt) * a_tile + (size_t)(tl + p.pad2 + p.pad1) * 16;
-                    const float rinv = p.in_slope != 0.f ? 1.0f / p.in_slope : 1.0f;
                     mbar_wait(&a_full[buf], (uint32_t)((p.abufs == 2 ? (tile >> 1) : tile) & 1));   // complete long ago: acquire the TMA's writes
                     // The output tile [2G][OV][16 B] aliases T1, which conv2's MMAs of BOTH M-tiles read (M-tile 0's rows reach
                     // into the second half and the two layouts interleave): every epilogue thread has passed its own
                     // m_full / c_full wait here, so after this barrier all of conv2 has retired.
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
                     RB_TS(2 + mt, tile * 8 + 5);
                     uint8_t* dst = t1 + (size_t)i * 16;
 #pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const uint4 xh = *reinterpret_cast<const uint4*>(xs + (size_t)g * XR1 * 16);
-                        const uint4 xl = *reinterpret_cast<const uint4*>(xs + (size_t)(G + g) * XR1 * 16);
+                    for (int gg = 0; gg < GH; ++gg) {
+                        const uint4 xh = *reinterpret_cast<const uint4*>(xs + (size_t)(g0 + gg) * XR1 * 16);
+                        const uint4 xl = *reinterpret_cast<const uint4*>(xs + (size_t)(G + g0 + gg) * XR1 * 16);
                         const uint32_t hh[4] = {xh.x, xh.y, xh.z, xh.w}, ll[4] = {xl.x, xl.y, xl.z, xl.w};
                         float o[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
                             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ll[j]));
-                            float x0 = (fh.x + fl.x) * (1.0f / TC_ASCALE), x1 = (fh.y + fl.y) * (1.0f / TC_ASCALE);
-                            x0 = x0 < 0.f ? x0 * rinv : x0;
-                            x1 = x1 < 0.f ? x1 * rinv : x1;
-                            float y0 = fmaf(racc[8 * g + 2 * j], isc, sbias[C + 8 * g + 2 * j]) + x0;
-                            float y1 = fmaf(racc[8 * g + 2 * j + 1], isc, sbias[C + 8 * g + 2 * j + 1]) + x1;
-                            if (p.out_act == ACT_LEAKY) {
-                                y0 = y0 < 0.f ? y0 * p.out_slope : y0;
-                                y1 = y1 < 0.f ? y1 * p.out_slope : y1;
-                            }
-                            ovf |= valid && (fabsf(y0) > 8000.f || fabsf(y1) > 8000.f);
-                            o[2 * j] = valid ? y0 : 0.f;
-                            o[2 * j + 1] = valid ? y1 : 0.f;
+                            float x0 = fh.x + fl.x, x1 = fh.y + fl.y;               // 8 * leaky(x)
+                            x0 = fminf(x0, x0 * rinv);
+                            x1 = fminf(x1, x1 * rinv);
+                            float y0 = fmaf(racc[8 * gg + 2 * j], isc2, sbias[C + c0 + 8 * gg + 2 * j]) + x0;
+                            float y1 = fmaf(racc[8 * gg + 2 * j + 1], isc2, sbias[C + c0 + 8 * gg + 2 * j + 1]) + x1;
+                            y0 = fmaxf(y0, y0 * oslope);
+                            y1 = fmaxf(y1, y1 * oslope);
+                            amax = fmaxf(amax, valid ? fmaxf(fabsf(y0), fabsf(y1)) : 0.f);
+                            o[2 * j] = y0; o[2 * j + 1] = y1;
                         }
                         if (i < OV) {
                             uint4 hi, lo;
-                            split8(o, hi, lo);
-                            *reinterpret_cast<uint4*>(dst + (size_t)g * OV * 16) = hi;
-                            *reinterpret_cast<uint4*>(dst + (size_t)(G + g) * OV * 16) = lo;
+                            split8_scaled(o, hi, lo);
+                            if (!valid) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
+                            *reinterpret_cast<uint4*>(dst + (size_t)(g0 + gg) * OV * 16) = hi;
+                            *reinterpret_cast<uint4*>(dst + (size_t)(G + g0 + gg) * OV * 16) = lo;
                         }
                     }
                     // the x tile has been read: after the barrier below it may be refilled (its other readers, conv1's MMAs,
                     // retired long ago)
                     fence_proxy_async();
                     RB_TS(2 + mt, tile * 8 + 6);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
                     if (tid < 2 * G) {        // one bulk store per (plane, 16-byte channel group): exactly the rows of this utterance
                         const int nrows = min(OV, it.len - it.t0);
                         __half* gdst = p.outp.base + ((size_t)tid * p.outp.rows_p + (size_t)(it.prow_u + it.t0)) * 8;
@@ -290,123 +482,66 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
             }
         }
         if (tid < 2 * G) bulk_wait_all0();
-        if (ovf && p.flags) atomicOr(p.flags, 1u);
-    } else if (warp == 8 || warp == 9) {
-        // ================= MMA issuers ================================================================
-        if (p.trace && blockIdx.x == 0 && lane == 0) rtr = p.trace;
-        const int role = warp - 8;                    // mode 0: 0 = main (A_hi x [W_hi|W_lo]), 1 = corr (A_lo x W_hi); mode 1: M-tile `role`
-        const uint32_t id_main = (1u << 4) | ((uint32_t)((p.mode ? C : 2 * C) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t id_corr = (1u << 4) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t b_lbo = 2 * C * 16;            // bytes between the two 8-channel groups of a K-step (merged stage: 2C rows)
-        const uint64_t b_bits = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-        const uint32_t w_s = smem_u32(wst);
-        uint32_t af_par[2] = {0, 0}, t1_par = 0, me_par[2] = {1, 1}, ce_par[2] = {1, 1};
-        int bs = 0; uint32_t bph = 0;                 // ring slot / phase
-        for (int tile = 0; rb_next(it, p.seg, OV); ++tile) {
-            const int buf = p.abufs == 2 ? (tile & 1) : 0;
-            for (int ph = 0; ph < 2; ++ph) {
-                const int k = ph ? p.k2 : p.k1, dil = ph ? 1 : p.d1;
-                const int XR = ph ? XR2 : XR1;
-                RB_TS(role, tile * 8 + ph * 3);
-                if (ph == 0) { mbar_wait_warp(&a_full[buf], af_par[buf]); af_par[buf] ^= 1; }
-                else { mbar_wait_warp(t1_full, t1_par); t1_par ^= 1; }
-                tc_fence_after();
-                RB_TS(role, tile * 8 + ph * 3 + 1);
-                const uint32_t a_lbo = (uint32_t)XR * 16;
-                const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-                const uint32_t a_lo = (uint32_t)G * a_lbo;            // lo plane follows the G groups of the hi plane
-                const int NU = p.mode ? 1 : (k + UPT - 1) / UPT;
-                const int sbase = p.resident ? (ph ? p.k1 : 0) : 0;
-                for (int un = 0; un < NU; ++un) {
-                    const int tap0 = un * UPT, tap1 = min(k, tap0 + UPT);
-                    const int bs0 = bs; const uint32_t bph0 = bph;
-                    for (int mt = 0; mt < 2; ++mt) {
-                        if (p.mode && mt != role) continue;
-                        const uint32_t a_s = ph ? smem_u32(t1) + (uint32_t)(mt * 128) * 16 : smem_u32(abuf) + (uint32_t)(buf * 2 + mt) * a_tile;
-                        const uint32_t tmain = tmem + (uint32_t)(mt * 3 * C), tcorr = tmain + 2 * C;
-                        if (p.mode || role == 0) { mbar_wait_warp(&m_empty[mt], me_par[mt]); me_par[mt] ^= 1; tc_fence_after(); }
-                        else if (un == 0) { mbar_wait_warp(&c_empty[mt], ce_par[mt]); ce_par[mt] ^= 1; tc_fence_after(); }
-                        if (!p.resident) { bs = bs0; bph = bph0; }     // both M-tile passes walk the same ring slots
-                        for (int tap = tap0; tap < tap1; ++tap) {
-                            int s;
-                            if (p.resident) {
-                                s = sbase + tap;
-                                if (tile == 0 && (mt == 0 || p.mode)) { mbar_wait_warp(&b_full[s], 0); tc_fence_after(); }
-                            } else {
-                                s = bs;
-                                if (mt == 0 || p.mode) { mbar_wait_warp(&b_full[s], bph); tc_fence_after(); }
-                                if (++bs == p.nb) { bs = 0; bph ^= 1; }
-                            }
-                            const uint64_t da = a_bits | (uint64_t)(((a_s + (uint32_t)(tap * dil) * 16) & 0x3FFFFu) >> 4);
-                            const uint64_t db = b_bits | (uint64_t)(((w_s + (uint32_t)s * stage) & 0x3FFFFu) >> 4);
-                            if (elect_one()) {
-#pragma unroll
-                                for (int ks = 0; ks < KS; ++ks) {
-                                    const uint64_t a = da + (uint32_t)(ks * ((2 * a_lbo) >> 4)), b = db + (uint32_t)(ks * ((2 * b_lbo) >> 4));
-                                    if (p.mode || role == 0) tc_mma_f16(tmain, a, b, id_main, (tap == tap0 && ks == 0) ? 0u : 1u);
-                                    else tc_mma_f16(tcorr, a + (a_lo >> 4), b, id_corr, (un == 0 && tap == 0 && ks == 0) ? 0u : 1u);
-                                }
-                                if (!p.resident && (mt == 1 || p.mode)) tc_commit(&b_empty[s]);
-                            }
-                            __syncwarp();
-                        }
-                        if (elect_one()) {
-                            if (p.mode || role == 0) tc_commit(&m_full[mt]);
-                            else if (un == NU - 1) tc_commit(&c_full[mt]);
-                        }
-                        __syncwarp();
-                    }
-                }
-                RB_TS(role, tile * 8 + ph * 3 + 2);
-            }
-        }
-    } else if (warp == 10) {
-        // ================= x-tile producer (TMA) ======================================================
+        if (amax > 65000.f && p.flags) atomicOr(p.flags, 1u);
+    } else if (warp < 20) {
+        // ================= MMA issuers: warp 16 + 2 KIND + mt, one thread each ========================
         if (lane == 0) {
-            uint32_t ae_par[2] = {1, 1};
-            for (int tile = 0; rb_next(it, p.seg, OV); ++tile) {
-                const int buf = p.abufs == 2 ? (tile & 1) : 0;
-                mbar_wait(&a_empty[buf], ae_par[buf]); ae_par[buf] ^= 1;
-                const long long r0 = it.prow_u + it.t0 - p.pad2 - p.pad1;      // >= prow_u - TC_GAP >= 0
-                mbar_expect_tx(&a_full[buf], 2 * a_tile);
-                tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
-                tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
-            }
+            const int kind = (warp - 16) >> 1, imt = (warp - 16) & 1;
+            if (p.trace && blockIdx.x == 0 && imt == 0) rtr = p.trace;
+            if (kind == 0) rb_issuer<C, 0>(p, imt, smem_u32(abuf), smem_u32(t1), smem_u32(wst), tmem, a_full, m_full, m_empty, c_full, c_empty, t1_full, b_full, b_empty, rtr);
+            else rb_issuer<C, 1>(p, imt, smem_u32(abuf), smem_u32(t1), smem_u32(wst), tmem, a_full, m_full, m_empty, c_full, c_empty, t1_full, b_full, b_empty, rtr);
         }
         __syncwarp();
     } else {
-        // ================= weight producer (bulk copies) ==============================================
+        // ================= producer: ONE thread feeds both the x tiles (TMA) and the weight stages (bulk copies) ==========
+        // cooperative polling (mbarrier.test_wait, never blocking on one stream while the other could advance)
         if (lane == 0) {
+            // x tiles
+            int xw = blockIdx.x, xtile = 0; uint32_t ae_par0 = 1, ae_par1 = 1;
+            // weights
+            int ww = blockIdx.x, wc = 0, wtap = 0, ws_ = 0; uint32_t wph = 1;
             if (p.resident) {
-                RbTile probe = it;
-                if (rb_next(probe, p.seg, OV)) {
-                    for (int s = 0; s < p.k1 + p.k2; ++s) {
-                        const uint8_t* src = s < p.k1 ? reinterpret_cast<const uint8_t*>(p.w1) + (size_t)s * stage
-                                                      : reinterpret_cast<const uint8_t*>(p.w2) + (size_t)(s - p.k1) * stage;
-                        mbar_expect_tx(&b_full[s], stage);
-                        bulk_g2s(wst + (size_t)s * stage, src, stage, &b_full[s]);
+                if ((int)blockIdx.x < W)
+                    for (int s2 = 0; s2 < p.k1 + p.k2; ++s2) {
+                        const uint8_t* src = s2 < p.k1 ? reinterpret_cast<const uint8_t*>(p.w1) + (size_t)s2 * stage
+                                                       : reinterpret_cast<const uint8_t*>(p.w2) + (size_t)(s2 - p.k1) * stage;
+                        mbar_expect_tx(&b_full[s2], stage);
+                        bulk_g2s(wst + (size_t)s2 * stage, src, stage, &b_full[s2]);
+                    }
+                ww = W;      // nothing more to stream
+            }
+            while (xw < W || ww < W) {
+                bool progress = false;
+                if (xw < W) {
+                    const int buf = p.abufs == 2 ? (xtile & 1) : 0;
+                    if (mbar_test(&a_empty[buf], buf ? ae_par1 : ae_par0)) {
+                        if (buf) ae_par1 ^= 1; else ae_par0 ^= 1;
+                        const RbTile it = rb_tile(p, xw);
+                        const long long r0 = it.prow_u + it.t0 - p.pad2 - p.pad1;      // >= prow_u - TC_GAP >= 0
+                        mbar_expect_tx(&a_full[buf], 2 * a_tile);
+                        tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
+                        tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
+                        xw += wstep; ++xtile;
+                        progress = true;
                     }
                 }
-            } else {
-                int s = 0; uint32_t ph = 1;
-                while (rb_next(it, p.seg, OV)) {
-                    for (int c = 0; c < 2; ++c) {
-                        const int k = c ? p.k2 : p.k1;
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(c ? p.w2 : p.w1);
-                        for (int tap = 0; tap < k; ++tap) {
-                            mbar_wait(&b_empty[s], ph);
-                            mbar_expect_tx(&b_full[s], stage);
-                            bulk_g2s(wst + (size_t)s * stage, src + (size_t)tap * stage, stage, &b_full[s]);
-                            if (++s == p.nb) { s = 0; ph ^= 1; }
-                        }
+                if (ww < W) {
+                    if (mbar_test(&b_empty[ws_], wph)) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(wc ? p.w2 : p.w1) + (size_t)wtap * stage;
+                        mbar_expect_tx(&b_full[ws_], stage);
+                        bulk_g2s(wst + (size_t)ws_ * stage, src, stage, &b_full[ws_]);
+                        if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
+                        if (++wtap == (wc ? p.k2 : p.k1)) { wtap = 0; if (++wc == 2) { wc = 0; ww += wstep; } }
+                        progress = true;
                     }
                 }
+                if (!progress) __nanosleep(32);
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols));
     }
@@ -493,7 +628,7 @@ inline bool rb_pair_eligible(const RbWeights& a, const RbWeights& b) {
     if (!a.ok || !b.ok) return false;
     if (b.dil != 1 || 2 * b.pad != b.k - 1 || 2 * a.pad != (a.k - 1) * a.dil) return false;
     if (a.pad + b.pad > TC_GAP || 128 + (a.k - 1) * a.dil > 256 || b.pad > a.pad) return false;
-    if (a.k + b.k > RB_MAX_STAGES || b.k > 33) return false;
+    if (a.k + b.k > RB_MAX_STAGES || b.k > 33 || a.k < 2 || b.k < 2) return false;
     return true;
 }
 struct RbPlan { size_t smem; int abufs, resident, nb; };
@@ -556,7 +691,10 @@ inline cudaError_t rb_device_setup() {
     return cudaFuncSetAttribute(rb_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 // x planes (act applied by the producer) -> x' planes.  Returns 1 (launches), < 0 on error.
-inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const Planes& in, const Planes& out, Seg seg, int nseg, int maxlen,
+// `tiles` / `ntiles`: the super-tile table of this segmentation for ov = rb_ov(b) rows per tile (rb_tiles_kernel; ntiles is computed
+// on the host from the same lengths).
+inline int rb_ov(const RbWeights& b) { return 256 - (b.k - 1); }
+inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const Planes& in, const Planes& out, Seg seg, const int2* tiles, int ntiles,
                           float in_slope, int out_act, float out_slope, int mode, int sms, unsigned int* flags, cudaStream_t stream) {
     if (!rb_pair_eligible(a, b) || in.C != C || out.C != C) return -3;
     RbP p;
@@ -574,10 +712,11 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
     p.in_slope = in_slope; p.out_act = out_act; p.out_slope = out_slope;
     p.tmem_cols = C == 32 ? 256 : 512;
     p.flags = flags;
-    const int gx = (maxlen + p.ov - 1) / p.ov;
-    const long long W = (long long)gx * nseg;
-    if (W <= 0 || W > 0x7fffffffLL) return -1;
-    p.gx = gx; p.work_items = (int)W;
+    static const int env_dbg = getenv("STTS_RB_DBG") ? atoi(getenv("STTS_RB_DBG")) : 0;
+    p.dbg = env_dbg;
+    const long long W = ntiles;
+    if (W <= 0 || !tiles) return -1;
+    p.tiles = tiles; p.work_items = ntiles;
     alignas(64) CUtensorMap imap;
     if (!rb_make_map(&imap, in, p.xr1)) return -1;
     p.outp = out;
@@ -592,7 +731,7 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
     static long long* trace_buf = nullptr;
     static const int env_trace = getenv("STTS_RB_TRACE") ? atoi(getenv("STTS_RB_TRACE")) : 0;   // k to trace (first matching launches per C)
     static int trace_left[2] = {1, 1};
-    const bool do_trace = env_trace && a.k == env_trace && a.dil == (a.k == 3 ? 1 : (a.k == 7 ? 3 : 5)) && trace_left[C == 64] > 0 && maxlen > 1024;
+    const bool do_trace = env_trace && a.k == env_trace && a.dil == (a.k == 3 ? 1 : (a.k == 7 ? 3 : 5)) && trace_left[C == 64] > 0 && ntiles > 296;
     if (do_trace && !trace_buf) cudaMalloc(&trace_buf, 6 * 1024 * 8);
     if (do_trace) cudaMemsetAsync(trace_buf, 0, 6 * 1024 * 8, stream);
     p.trace = do_trace ? trace_buf : nullptr;
@@ -610,6 +749,11 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, " %s:", names[r]);
             for (int i = 0; i < 64; ++i) if (h[r * 1024 + i]) fprintf(stderr, " %d:%lld", i, h[r * 1024 + i] - t0);
+            fprintf(stderr, "\n");
+        }
+        for (int r = 4; r < 6; ++r) {      // per-tap issue timeline of tile 1: (before elect, after syncwarp) pairs
+            fprintf(stderr, " taps%d:", r - 4);
+            for (int i = 0; i < 200; ++i) if (h[r * 1024 + i]) fprintf(stderr, " %lld", h[r * 1024 + i] - t0);
             fprintf(stderr, "\n");
         }
     }
