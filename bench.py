@@ -198,7 +198,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
     ap.add_argument("--ids", type=int, default=128, help="phoneme ids per utterance")
     ap.add_argument("--durations", default="forced5", choices=["forced5", "model"])
-    ap.add_argument("--tensor", type=int, default=-1, help="-1 library default, 0 fp32 FFMA tiles only, 1 tcgen05 path")
+    ap.add_argument("--tensor", type=int, default=-1, help="-1 library default (1), 0 fp32 FFMA tiles only, 1 tcgen05 split-fp16 "
+                    "(fp32-accurate), 2 tcgen05 throughput mode (one fp16 MMA per K-step)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch utterances per GPU; strong: --batch utterances in total, split over the ranks (BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -208,6 +211,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncpu = host_cores()
 
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of ranks")
+        args.batch //= world
     blob, wkind, mfile = get_model(args.model)
     from summertts_b200 import binfmt
 
@@ -217,7 +224,11 @@ def main():
     workload = "%s (%s weights), %d utterances x %d synthetic phoneme ids per GPU, %s" % (
         args.model, wkind, args.batch, args.ids,
         "forced 5 frames/id (163840 samples/utt)" if forced_per_id else "model-predicted durations")
+    tmode = 1 if args.tensor < 0 else args.tensor
+    dtype = {0: "f32", 1: "f32", 2: "f16"}[tmode]
     config = {"workload": workload, "batch_per_gpu": args.batch, "ids_per_utt": args.ids,
+              "arithmetic": {0: "fp32 FFMA tiles", 1: "split-fp16 tcgen05 MMAs (3 per K-step), fp32 accumulate + fp32 promotion: fp32-accurate",
+                             2: "throughput mode: one fp16 tcgen05 MMA per K-step, fp32 accumulate"}[tmode],
               "durations": "forced5" if forced_per_id else "model", "l2": "flushed (256 MiB write) before every timed step",
               "parallelism": "replicas x%d, no collective" % world}
 
@@ -228,7 +239,7 @@ def main():
         v, workers, sec, table = run_cpu_best(mfile, args.ids, vocab, forced_per_id, ncpu, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "audio_samples_per_sec", "value": v, "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic ids; %s weights" % wkind, "config": config, "rtf": SR / v,
                 "cpu_baseline": {"value": v, "unit": "samples/s", "cores": workers, "kind": "reference",
                                  "cores_allowed": ncpu, "cores_logical": os.cpu_count(), "cpu_model": cpu_model(),
@@ -337,8 +348,9 @@ def main():
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+        if os.path.exists(tp) and args.model == "single_speaker_fast" and args.batch == 64 and args.ids == 128:
+            tj = json.load(open(tp))        # ncu DRAM bytes per launch of the class, captured on the default workload
+            traffic = tj.get("%s@t%d" % (dom, tmode), tj.get(dom) if tmode == 1 else None)
         roof = {"bound": "tensor", "kernel_class": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach / peak_tf, "traffic": traffic, "peak_source": how + " bf16 sustained",
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1),
@@ -379,13 +391,13 @@ def main():
         v = S_all * args.steps / (ms * 1e-3)
         ve = S_all * args.steps / (ms_e2e * 1e-3)
         line = {"metric": "audio_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic ids; %s weights" % wkind, "config": config,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic ids; %s weights" % wkind, "config": config,
                 "clocks": clocks,
                 "e2e": {"value": ve, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(ids.nbytes + offs.nbytes + 8 * args.batch + 8),
                         "d2h_bytes_per_step": int(2 * S + 4 * args.batch)},
-                "gpu_launches": int(launches), "rtf": SR / v, "x_realtime_per_gpu": v / world / SR,
+                "gpu_launches": int(launches), "tensor_fallbacks": E.tensor_fallbacks(), "rtf": SR / v, "x_realtime_per_gpu": v / world / SR,
                 "samples_per_step": S_all, "stage_ms_last_step": stage_ms, "roofline": roof,
                 "conv_classes": {k: {"ms": round(x["ms"] / 2, 4), "tflops": (x["flops"] / (x["ms"] * 1e-3) / 1e12) if x["ms"] > 0 else 0,
                                      "launches": x["launches"] // 2} for k, x in prof.items() if x["launches"]},

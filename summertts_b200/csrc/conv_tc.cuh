@@ -343,6 +343,8 @@ struct TcP {
     const float* acc_src;   // EPI_ACCUM / EPI_ACCUM_DIV: accumulate onto this tensor instead of y (null: y itself)
     long long* trace;   // optional clock64 trace of one CTA (tools/tc_trace.py): [5 roles][1024]
     int dbg;            // timing experiments (STTS_TC_DBG): 1 = skip activation TMA after warm-up, 2 = skip epilogue stores
+    int single;         // throughput mode (stts_set_tensor_path(2)): ONE fp16 MMA per K-step (hi x hi only); the correction MMAs are
+                        // not issued and the correction accumulator is not added (the barrier protocol is unchanged)
 };
 
 constexpr int TC_MAX_BSTAGES = 48;
@@ -559,7 +561,10 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                 for (int cb = 0; cb < NC; cb += 16) {
                     float v[16], x2[16];
                     tc_ld16(tmain + cb, v);
-                    tc_ld16(tmain + NC + cb, x2);
+                    if (t.single) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x2[j] = 0.f;
+                    } else tc_ld16(tmain + NC + cb, x2);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) racc[cb + j] = v[j] + x2[j];
                 }
@@ -604,11 +609,14 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                 // correction MMAs then overlap this tile's global-memory epilogue (warp-collective TMEM loads: all
                 // lanes participate even for rows past the end)
 #pragma unroll
-                for (int cb = 0; cb < NC; cb += 16) {
-                    float v[16];
-                    tc_ld16(tcorr + cb, v);
+                if (!t.single) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
+                    for (int cb = 0; cb < NC; cb += 16) {
+                        float v[16];
+                        tc_ld16(tcorr + cb, v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) racc[cb + j] += v[j];
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&c_empty[ci]);
@@ -618,8 +626,11 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                 float v[16];
                 if (SU) {
                     float m[16];
-                    tc_ld16(tcorr + cb, v);
                     tc_ld16(tmain + cb, m);
+                    if (t.single) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    } else tc_ld16(tcorr + cb, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = m[j] + v[j];
                 } else {
@@ -768,7 +779,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
         {
             // instruction descriptor: D=f32, A=B=f16, K-major both, N>>3, M>>4 (M = 128)
             // merged mode: the hi*hi|hi*lo MMA is N = 2*NC wide over B' = [B_hi ; B_lo]; the lo*hi MMA reads rows 0..NC-1 of B'
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(((MG && do_main) ? 2 * NCW : NCW) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(((MG && do_main && !t.single) ? 2 * NCW : NCW) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t a_s = smem_u32(a_ring), b_s = smem_u32(bst);
             const uint32_t a_lbo = (uint32_t)XR * 16, b_lbo = (uint32_t)(MG ? 2 * NCW : NCW) * 16;
             // descriptors are built once and only their 14-bit start-address field (units of 16 B) is advanced
@@ -830,7 +841,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                             if (k16 < nk16) {
                                 const uint64_t a = dah + (uint32_t)(k16 * a_k16), b = dbh + (uint32_t)(k16 * b_k16);
                                 if (do_main) tc_mma_f16(tmain, a, b, idesc, k16 == 0 ? main_acc : 1u);
-                                else {
+                                else if (!t.single) {
                                     tc_mma_f16(tcorr, a + a_lo_off, b, idesc, k16 == 0 ? corr_acc : 1u);
                                     if (!MG) tc_mma_f16(tcorr, a, b + b_lo_off, idesc, 1);
                                 }
@@ -996,8 +1007,9 @@ inline cudaError_t tc_device_setup() {
     return cudaSuccess;
 }
 inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, const TcOut& out, int nseg, int maxlen,
-                          cudaStream_t stream, int sms_dev = 0) {
+                          cudaStream_t stream, int sms_dev = 0, int single_mma = 0) {
     TcP t;
+    t.single = single_mma;
     static const int env_span = getenv("STTS_TC_SPAN") ? atoi(getenv("STTS_TC_SPAN")) : 0;
     t.usteps = w.usteps; t.span = env_span;
     t.wp = w.packed; t.NC = w.NC; t.nchunks = w.nchunks; t.kchunks = w.kchunks; t.KC = w.KC; t.inv_scale = w.inv_scale;

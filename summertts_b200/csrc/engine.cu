@@ -419,7 +419,10 @@ struct stts_engine {
             if (o.out2_planes) out.y2p = *o.out2_planes;
             out.out_act = o.out_act; out.out_slope = o.out_slope; out.write_f32 = o.write_f32;
             out.y_tt = o.y_tt; out.y2_tt = o.y2_tt; out.res_tt = o.res_tt; out.acc_tt = o.acc_tt; out.acc_src = o.acc_src;
-            const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream, sms);
+            const int r = tc_conv_launch(c.tc, p, in, out, nseg, maxlen, stream, sms,
+                                         // throughput mode covers the frame-level layers only: the text encoder and the duration predictor keep the
+                                         // fp32-accurate MMAs, because ceil(exp(logw) * length_scale) must not move (SynthesizerTrn.cpp:376-378)
+                                         (tensor_mode == 2 && curCls >= STTS_CLS_FLOW_IO) ? 1 : 0);
             if (r == -2) throw std::runtime_error("tile-transposed tensor with a row stride (planning bug)");
             if (r < 0) throw CudaError("cuTensorMapEncodeTiled failed for an activation plane");
             launches += r;

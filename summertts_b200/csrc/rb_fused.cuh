@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) rb_tiles_kernel(Seg seg, int nseg, int ov
 //   mode 0: ROLE 0 issues A_hi x [W_hi | W_lo] (N = 2C) into main[mt], ROLE 1 issues A_lo x W_hi (N = C) into corr[mt];
 //   mode 1: ROLE r issues A_hi x W_hi (N = C) for M-tile r.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int rb_nmain(int C) { return C == 32 ? 2 : 1; }
 template <int C, int KIND>
 __device__ __forceinline__ void rb_issuer(const RbP& p, const int mt, const uint32_t abuf_s, const uint32_t t1_s, const uint32_t w_s, const uint32_t tmem,
                                           uint64_t* a_full, uint64_t* m_full, uint64_t* m_empty, uint64_t* c_full, uint64_t* c_empty,
@@ -165,12 +166,15 @@ __device__ __forceinline__ void rb_issuer(const RbP& p, const int mt, const uint
     constexpr uint32_t b_lbo = 2 * C * 16;        // bytes between the two 8-channel groups of a K-step (merged stage: 2C rows)
     constexpr uint32_t b_k16 = (2 * b_lbo) >> 4;
     const uint64_t b_desc0 = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46) | (uint64_t)((w_s & 0x3FFFFu) >> 4);
-    uint32_t af_par0 = 0, af_par1 = 0, t1_par = 0, e_par = 1;
+    uint32_t af_par0 = 0, af_par1 = 0, t1_par = 0, e_par0 = 1, e_par1 = 1;
     int bs = 0; uint32_t bph = 0;                 // ring slot / phase
     const int W = p.work_items, step = gridDim.x;
-    const uint32_t d_t = tmem + (uint32_t)(mt * 3 * C) + (KIND == 1 ? 2 * C : 0);
-    uint64_t* full_bar = KIND == 0 ? &m_full[mt] : &c_full[mt];
-    uint64_t* empty_bar = KIND == 0 ? &m_empty[mt] : &c_empty[mt];
+    // TMEM per M-tile: main[NMAIN] (2C columns each) then corr (C columns).  With two main accumulators (C = 32: TMEM has the
+    // room) the KIND 0 issuer runs two promotion units ahead of the drains, so conv1 of the next tile overlaps epilogue 2.
+    constexpr int NMAIN = rb_nmain(C);
+    constexpr uint32_t MT_COLS = (2 * NMAIN + 1) * C;
+    const uint32_t d_base = tmem + (uint32_t)mt * MT_COLS;
+    uint32_t ucount = 0;                            // units issued by this thread (selects the main accumulator)
     const int tstep = mode ? 2 : 1, toff = mode ? KIND : 0;     // mode 1: this issuer's taps are toff, toff + 2, ...
     int tile = 0;
 #ifdef STTS_TC_TRACE_BUILD
@@ -199,7 +203,12 @@ __device__ __forceinline__ void rb_issuer(const RbP& p, const int mt, const uint
 #pragma unroll 1
             for (int un = 0; un < NU; ++un) {
                 const int tap0 = (NU == 1 ? 0 : un * UPT) + toff, tap1 = NU == 1 ? k : min(k, un * UPT + UPT);
-                mbar_wait(empty_bar, e_par); e_par ^= 1;          // accumulator drained by the epilogue sets
+                const uint32_t mb = (KIND == 0 && NMAIN == 2) ? (ucount & 1u) : 0u;
+                ++ucount;
+                uint64_t* full_bar = KIND == 0 ? &m_full[mt * 2 + mb] : &c_full[mt];
+                uint64_t* empty_bar = KIND == 0 ? &m_empty[mt * 2 + mb] : &c_empty[mt];
+                const uint32_t d_t = d_base + (KIND == 1 ? (uint32_t)(2 * NMAIN * C) : mb * 2 * C);
+                if (mb) { mbar_wait(empty_bar, e_par1); e_par1 ^= 1; } else { mbar_wait(empty_bar, e_par0); e_par0 ^= 1; }   // accumulator drained
                 tc_fence_after();
                 uint64_t da = a_bits | (uint64_t)(((a_s + (uint32_t)tap0 * dil * 16) & 0x3FFFFu) >> 4);
                 uint32_t acc = 0u;
@@ -297,12 +306,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)p.nb * stage);
     uint64_t* a_full = bars;             // [2]
     uint64_t* a_empty = bars + 2;        // [2]
-    uint64_t* m_full = bars + 4;         // [2] per M-tile
-    uint64_t* m_empty = bars + 6;        // [2]
-    uint64_t* c_full = bars + 8;         // [2]
-    uint64_t* c_empty = bars + 10;       // [2]
-    uint64_t* t1_full = bars + 12;       // [1]
-    uint64_t* b_full = bars + 13;        // [RB_MAX_STAGES]
+    uint64_t* m_full = bars + 4;         // [2 M-tiles][2 main accumulators]
+    uint64_t* m_empty = bars + 8;        // [2][2]
+    uint64_t* c_full = bars + 12;        // [2]
+    uint64_t* c_empty = bars + 14;       // [2]
+    uint64_t* t1_full = bars + 16;       // [1]
+    uint64_t* b_full = bars + 17;        // [RB_MAX_STAGES]
     uint64_t* b_empty = b_full + RB_MAX_STAGES;   // [RB_MAX_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + RB_MAX_STAGES);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);   // [2][C], x8 domain
@@ -310,7 +319,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 4);      // one arrival per epilogue set (M-tile, column half)
-            mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 8);      // one arrival per warp of the M-tile's two sets
+            mbar_init(&m_full[2 * i], 1); mbar_init(&m_empty[2 * i], 8);      // one arrival per warp of the M-tile's two sets
+            mbar_init(&m_full[2 * i + 1], 1); mbar_init(&m_empty[2 * i + 1], 8);
             mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 8);
         }
         mbar_init(t1_full, 16);                                        // one arrival per epilogue warp
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;      // M-tile mt: main @ mt*3C (2C columns: hi*hi | hi*lo), corr @ mt*3C + 2C (C columns)
+    const uint32_t tmem = *tmem_slot;      // per M-tile: main[NMAIN] (2C columns each: hi*hi | hi*lo) then corr (C columns)
 
     const int W = p.work_items, wstep = gridDim.x;
     long long* rtr = nullptr;
@@ -338,8 +348,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
         const int wq = warp & 3, mt = (warp >> 2) & 1, hf = warp >> 3;
         const int tl = wq * 32 + lane;                 // TMEM lane = row inside the M-tile
         const int c0 = hf * CH, g0 = hf * GH;
-        const uint32_t tmain = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * 3 * C + c0);
-        const uint32_t tcorr = tmain + 2 * C;
+        constexpr int NMAIN = rb_nmain(C);
+        constexpr uint32_t MT_COLS = (2 * NMAIN + 1) * C;
+        const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)mt * MT_COLS + (uint32_t)c0;
+        const uint32_t tcorr = tbase + 2 * NMAIN * C;
+        uint32_t ucount = 0, mf_par1 = 0;
         if (p.trace && blockIdx.x == 0 && tl == 0 && hf == 0) rtr = p.trace;
         uint32_t mf_par = 0, cf_par = 0;
         float amax = 0.f;                               // largest |8 x| converted (overflow check of the saturating split)
@@ -355,7 +368,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                 const int k = ph ? p.k2 : p.k1;
                 const int NU = p.mode ? 1 : (k + UPT - 1) / UPT;
                 for (int un = 0; un < NU; ++un) {
-                    mbar_wait_all(&m_full[mt], mf_par); mf_par ^= 1;
+                    const uint32_t mb = NMAIN == 2 ? (ucount & 1u) : 0u;
+                    ++ucount;
+                    const uint32_t tmain = tbase + mb * 2 * C;
+                    if (mb) { mbar_wait_all(&m_full[mt * 2 + 1], mf_par1); mf_par1 ^= 1; } else { mbar_wait_all(&m_full[mt * 2], mf_par); mf_par ^= 1; }
                     tc_fence_after();
                     if (un == 0) RB_TS(2 + mt, tile * 8 + ph * 3);
 #pragma unroll
@@ -377,7 +393,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&m_empty[mt]);
+                    if (lane == 0) mbar_arrive(&m_empty[mt * 2 + mb]);
                 }
                 {
                     mbar_wait_all(&c_full[mt], cf_par); cf_par ^= 1;
@@ -636,7 +652,7 @@ inline RbPlan rb_plan(int C, const RbWeights& a, const RbWeights& b, size_t budg
     RbPlan pl;
     const size_t xr1 = 128 + (size_t)(a.k - 1) * a.dil, xr2 = 256 + b.k - 1;
     const size_t a_tile = (size_t)C * xr1 * 4, t1 = (size_t)C * xr2 * 4, stage = (size_t)4 * C * C;
-    const size_t misc = (13 + 2 * RB_MAX_STAGES) * 8 + 16 + 2 * C * 4 + 256;
+    const size_t misc = (17 + 2 * RB_MAX_STAGES) * 8 + 16 + 2 * C * 4 + 256;
     const size_t wres = (size_t)(a.k + b.k) * stage;
     static const int e_ab = getenv("STTS_RB_ABUFS") ? atoi(getenv("STTS_RB_ABUFS")) : 0;
     static const int e_res = getenv("STTS_RB_RES") ? atoi(getenv("STTS_RB_RES")) : -1;
@@ -710,7 +726,7 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
     if (pl.smem > 227 * 1024 || (!pl.resident && pl.nb < std::min(upt_l, std::max(a.k, b.k)) + 1)) return -4;
     p.abufs = pl.abufs; p.resident = pl.resident; p.nb = pl.nb;
     p.in_slope = in_slope; p.out_act = out_act; p.out_slope = out_slope;
-    p.tmem_cols = C == 32 ? 256 : 512;
+    p.tmem_cols = 512;
     p.flags = flags;
     static const int env_dbg = getenv("STTS_RB_DBG") ? atoi(getenv("STTS_RB_DBG")) : 0;
     p.dbg = env_dbg;

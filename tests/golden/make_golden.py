@@ -73,7 +73,13 @@ def main():
             print("skip", name)
             continue
         M = binfmt.parse_model(blob)
-        ids = np.array(TEST_TXT_IDS if M["langType"] == 0 else synth_ids(rng, 96, vocab=M["enc"]["vocab"]), dtype=np.int32)
+        # CHS models: the ids of /root/reference/test.txt; ENG: the 700 ids of /root/reference/test_eng.txt (BASELINE config 4),
+        # both through the reference's own text frontend (summertts_b200/host/_build/tts_b200 --dump-ids, committed as
+        # tests/golden/test_eng_ids.txt)
+        if M["langType"] == 0:
+            ids = np.array(TEST_TXT_IDS, dtype=np.int32)
+        else:
+            ids = np.array(open(os.path.join(HERE, "test_eng_ids.txt")).read().split(), dtype=np.int32)
         R = ref.RefModel(blob)
         r = R.infer(ids, sid=sid, length_scale=ls)
         np.savez_compressed(os.path.join(HERE, "real_%s.npz" % name), ids=ids, sid=sid, ls=np.float32(ls),
