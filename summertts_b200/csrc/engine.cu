@@ -194,6 +194,7 @@ struct stts_engine {
     int64_t St = 0;
     std::vector<int64_t> h_soff;
     int16_t* d_pcm = nullptr;
+    bool runValid = false;       // the last run() completed: d_pcm / dbg / h_soff describe it
     struct Dbg {
         float *xx = nullptr, *m = nullptr, *logw = nullptr, *wceil = nullptr, *zp = nullptr, *z = nullptr, *o = nullptr;
     } dbg;
@@ -733,6 +734,13 @@ void stts_engine::ensure_ws(size_t bytes) {
 // ---------------------------------------------------------------------------------------------
 void stts_engine::stage(int B_, const int32_t* ids, const int32_t* offs, const int32_t* sids, const float* ls) {
     if (B_ <= 0 || !ids || !offs) throw ArgError("empty batch or null ids/offsets");
+    // a new batch invalidates the results of the previous run (stts_batch_fetch / stts_debug_fetch then report STTS_E_ARG)
+    St = 0; d_pcm = nullptr; dbg = Dbg(); h_soff.clear(); runValid = false;
+    if (ls)
+        for (int u = 0; u < B_; ++u)
+            if (!(ls[u] > 0.f) || !std::isfinite(ls[u]) || ls[u] > 1000.f) throw ArgError("length_scale must be finite, positive and <= 1000");
+    for (float w : forced)
+        if (!(w >= 0.f) || w > 65536.f) throw ArgError("forced durations must be finite, non-negative and <= 65536 frames");
     if (offs[0] != 0) throw ArgError("id_offsets[0] must be 0");
     int mt = 0;
     for (int u = 0; u < B_; ++u) {
@@ -746,17 +754,18 @@ void stts_engine::stage(int B_, const int32_t* ids, const int32_t* offs, const i
         if (ids[i] < 0 || ids[i] >= vocab) throw ArgError("phoneme id out of range at position " + std::to_string(i));
     if ((size_t)T > stageCapTok || (size_t)B_ > stageCapB) {
         CUDA_CHECK(cudaStreamSynchronize(stream));
-        auto re = [&](auto*& p, size_t n) {
-            if (p) CUDA_CHECK(cudaFree(p));
+        auto re = [&](auto*& p, size_t n) {      // the pointer is nulled before the new allocation: a failed cudaMalloc leaves no dangling pointer
+            if (p) { void* old = p; p = nullptr; CUDA_CHECK(cudaFree(old)); }
             void* q = nullptr;
             CUDA_CHECK(cudaMalloc(&q, n));
             p = (std::remove_reference_t<decltype(p)>)q;
         };
-        stageCapTok = std::max<size_t>(stageCapTok, (size_t)T * 2);
-        stageCapB = std::max<size_t>(stageCapB, (size_t)B_ * 2);
-        re(d_ids, stageCapTok * 4); re(d_forced, stageCapTok * 4);
-        re(d_toff, (stageCapB + 1) * 4); re(d_foff, (stageCapB + 1) * 4); re(d_nfr, stageCapB * 4);
-        re(d_sids, stageCapB * 4); re(d_ls, stageCapB * 4); re(d_bseg, 2 * 4);
+        const size_t capTok = std::max<size_t>(stageCapTok, (size_t)T * 2), capB = std::max<size_t>(stageCapB, (size_t)B_ * 2);
+        stageCapTok = 0; stageCapB = 0;          // raised only after every allocation succeeded
+        re(d_ids, capTok * 4); re(d_forced, capTok * 4);
+        re(d_toff, (capB + 1) * 4); re(d_foff, (capB + 1) * 4); re(d_nfr, capB * 4);
+        re(d_sids, capB * 4); re(d_ls, capB * 4); re(d_bseg, 2 * 4);
+        stageCapTok = capTok; stageCapB = capB;
     }
     B = B_; Tt = T; maxT = mt;
     h_toff.assign(offs, offs + B + 1);
@@ -782,6 +791,7 @@ void stts_engine::stage(int B_, const int32_t* ids, const int32_t* offs, const i
 // ---------------------------------------------------------------------------------------------
 void stts_engine::run() {
     if (B <= 0) throw ArgError("no batch staged");
+    runValid = false;
     const int H = hidden;
     const Seg tseg{d_toff, 1, 0};
     const Seg bseg{d_bseg, 1, 0};
@@ -792,7 +802,12 @@ void stts_engine::run() {
     size_t ffnW = 0, dpW = 0;
     for (auto& L : enc) ffnW = std::max<size_t>(ffnW, L.f1.Cout);
     dpW = durPredType == 1 ? (size_t)std::max(dp1.Cout, dp2.Cout) : (size_t)H;
-    size_t tokFloats = (size_t)Tt * (H * 5 + 3 * H + 2 * ffnW + inter + 3 * dpW + 64 + 8) + (size_t)B * (gin + 4096 + 2 * 64 * ffnW) + 512 * ffnW + 4096;
+    size_t condFloats = 64;      // per-utterance conditioning vectors: speaker embedding + DP / decoder / per-flow WN cond outputs (+ 256 B padding each)
+    if (isMS) {
+        condFloats += (size_t)gin + 64 + (size_t)H + 64 + (size_t)convPre.Cout + 64;
+        for (auto& L : flow) if (L.hasCond) condFloats += (size_t)L.cond.Cout + 64;
+    }
+    size_t tokFloats = (size_t)Tt * (H * 5 + 3 * H + 2 * ffnW + inter + 3 * dpW + 64 + 8) + (size_t)B * (condFloats + 2 * 64 * ffnW) + 512 * ffnW + 4096;
     ensure_ws(tokFloats * 4 + (1 << 20));
     ws.reset();
     float* x = ws.get<float>((size_t)Tt * H);
@@ -932,6 +947,7 @@ void stts_engine::run() {
         maxF = std::max(maxF, hostInts[u]);
     }
     Ft = h_foff[B];
+    if (Ft <= 0 || (int64_t)Ft > (int64_t)16 << 20) throw ArgError("implausible frame count (length_scale / forced durations too large?)");
     CUDA_CHECK(cudaMemcpyAsync(d_foff, h_foff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaEventRecord(ev[2], stream));
 
@@ -1248,6 +1264,7 @@ void stts_engine::run() {
     h_soff.assign(B + 1, 0);
     for (int u = 0; u <= B; ++u) h_soff[u] = (int64_t)h_foff[u] * sMul;
     dbg.xx = x; dbg.m = mbuf; dbg.logw = logw; dbg.wceil = wceil; dbg.zp = zp_dbg; dbg.z = z; dbg.o = o;
+    runValid = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1389,6 +1406,7 @@ int stts_batch_run(stts_engine* e, int64_t* total) {
 int stts_batch_fetch(stts_engine* e, int16_t* pcm, int64_t cap, int64_t* soff) {
     return guard([&] {
         if (!e || !pcm) throw ArgError("null engine / buffer");
+        if (!e->runValid || !e->d_pcm) throw ArgError("no completed run to fetch from");
         if (e->St > cap) throw ArgError("pcm buffer too small");
         CUDA_CHECK(cudaSetDevice(e->device));
         CUDA_CHECK(cudaMemcpyAsync(pcm, e->d_pcm, (size_t)e->St * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -1421,10 +1439,14 @@ int stts_infer_batch(stts_engine* e, int32_t B, const int32_t* ids, const int32_
         }
         CUDA_CHECK(cudaMemcpyAsync(e->hostPcm, e->d_pcm, (size_t)e->St * 2, cudaMemcpyDeviceToHost, e->stream));
         CUDA_CHECK(cudaStreamSynchronize(e->stream));
+        for (int u = 0; u < B; ++u) pcm[u] = nullptr;
         for (int u = 0; u < B; ++u) {
             const int64_t n = e->h_soff[u + 1] - e->h_soff[u];
             pcm[u] = (int16_t*)malloc(std::max<int64_t>(n, 1) * 2);   // malloc'd like SynthesizerTrn.cpp:391
-            if (!pcm[u]) throw std::bad_alloc();
+            if (!pcm[u]) {
+                for (int v = 0; v < u; ++v) { free(pcm[v]); pcm[v] = nullptr; }
+                throw std::bad_alloc();
+            }
             memcpy(pcm[u], e->hostPcm + e->h_soff[u], (size_t)n * 2);
             ns[u] = (int32_t)n;
         }
@@ -1439,7 +1461,7 @@ int stts_infer_ids(stts_engine* e, const int32_t* ids, int32_t n, int32_t sid, f
 int stts_debug_fetch(stts_engine* e, int32_t which, float** out, int64_t* rows, int64_t* cols) {
     return guard([&] {
         if (!e || !out || !rows || !cols) throw ArgError("null argument");
-        if (e->B <= 0 || !e->dbg.xx) throw ArgError("no run to fetch from");
+        if (e->B <= 0 || !e->runValid || !e->dbg.xx) throw ArgError("no completed run to fetch from");
         const int T0 = e->h_toff[1] - e->h_toff[0], F0 = e->h_foff[1] - e->h_foff[0];
         const float* src = nullptr;
         int64_t r = 0, c = 1;

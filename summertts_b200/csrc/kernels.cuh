@@ -638,8 +638,9 @@ __global__ void __launch_bounds__(256) durations_kernel(const float* __restrict_
             if (forced) wc = forced[t0 + i];
             else wc = ceilf(expf(logw[(size_t)(t0 + i) * ldlogw]) * ls);
             w_ceil[t0 + i] = wc;
-            w = (int)wc;
-            if (w < 0) w = 0;
+            // NaN / inf / huge values (a cast of those is undefined) are clamped: at most 65536 frames per token; the host
+            // rejects implausible totals before it plans the frame-level workspace
+            w = (wc >= 0.f && wc <= 65536.f) ? (int)wc : (wc > 65536.f ? 65536 : 0);
         }
         part[threadIdx.x] = w;
         __syncthreads();

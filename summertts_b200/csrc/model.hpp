@@ -21,9 +21,11 @@ struct FormatError : std::runtime_error {
 struct Cursor {
     const float* p;
     int64_t n, o = 0;
-    int32_t i() {
+    int32_t i() {      // integer stored as float: must be finite and representable (a cast of NaN / inf / 1e30 is undefined)
         need(1);
-        return (int32_t)p[o++];
+        const float v = p[o++];
+        if (!(v > -2147483648.0f && v < 2147483648.0f)) throw FormatError("non-integer header value at float offset " + std::to_string(o - 1));
+        return (int32_t)v;
     }
     const float* f(int64_t cnt) {
         need(cnt);
@@ -197,10 +199,13 @@ inline GenRec parse_gen(Cursor& c, int decType, int isMS) {
     for (int i = 0; i < nUp; ++i) g.upRates.push_back(c.i());
     g.upInitCh = c.i();
     int nUpK = c.i();
+    if (nUpK < 0 || nUpK > 64) throw FormatError("implausible upsample kernel count");
     for (int i = 0; i < nUpK; ++i) g.upK.push_back(c.i());
     int nRbK = c.i();
+    if (nRbK < 1 || nRbK > 16) throw FormatError("implausible resblock kernel count");
     for (int i = 0; i < nRbK; ++i) g.rbK.push_back(c.i());
     int nRbD = c.i();
+    if (nRbD < 0 || nRbD > 64 || (nRbD != 0 && nRbD != nRbK)) throw FormatError("resblock dilation list does not match the kernel list");
     for (int i = 0; i < nRbD; ++i) { int a = c.i(), b = c.i(), d = c.i(); g.rbD.push_back({a, b, d}); }
     if (nUpK < nUp) throw FormatError("fewer upsample kernel sizes than rates");
     g.conv_pre = parse_conv(c);
