@@ -23,6 +23,7 @@
 #ifdef STTS_WITH_TC
 #include "conv_tc.cuh"
 #include "rb_fused.cuh"
+#include "pc_fused.cuh"
 #endif
 
 namespace stts {
@@ -58,6 +59,7 @@ struct DConv {
 #ifdef STTS_WITH_TC
     TcWeights tc;        // split-fp16 UMMA-layout copy (filled when the layer is tensor-path eligible)
     RbWeights rb;        // merged split-fp16 stages for the fused ResBlock1-pair kernel (rb_fused.cuh), ResBlock1 convs only
+    PcWeights pc;        // 64-column chunk stages for the staged-epilogue wide conv (pc_fused.cuh), WN in_layers / res_skip only
 #endif
 };
 struct DLN {
@@ -277,7 +279,7 @@ struct stts_engine {
     // Build a dense conv in device layout [k][Cin'][CoutW'] from a file record W[o][k][c].
     // omap[new_o] = orig_o, cmap[new_c] = orig_c (identity when empty); sign scales w and b.
     DConv make_conv(const ConvRec& r, const std::vector<int>& omap = {}, const std::vector<int>& cmap = {},
-                    float sign = 1.f, int padl = -1, bool tc_ok = true, bool rb_pair = false) {
+                    float sign = 1.f, int padl = -1, bool tc_ok = true, bool rb_pair = false, bool pc_wide = false) {
         if (r.sep) throw Unsupported("depthwise record passed to dense conv builder");
         DConv d;
         d.Cout = omap.empty() ? r.outCh : (int)omap.size();
@@ -306,8 +308,9 @@ struct stts_engine {
 #ifdef STTS_WITH_TC
         if (tc_ok) tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
         if (rb_pair && d.Cin == d.Cout) rb_prepare_weights(d.rb, w.data(), d.k, d.Cin, d.CoutW, d.dil, d.padl, d.b, owned);
+        if (pc_wide) pc_prepare_weights(d.pc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, d.dil, d.padl, d.b, owned);
 #else
-        (void)tc_ok; (void)rb_pair;
+        (void)tc_ok; (void)rb_pair; (void)pc_wide;
 #endif
         return d;
     }
@@ -495,6 +498,7 @@ struct stts_engine {
 #ifdef STTS_WITH_TC
         CUDA_CHECK(tc_device_setup());
         CUDA_CHECK(rb_device_setup());
+        CUDA_CHECK(pc_device_setup());
 #endif
     }
 #ifdef STTS_WITH_TC
@@ -631,11 +635,11 @@ void stts_engine::build(const Model& M) {
             if (in.outCh != 2 * H || in.inCh != H) throw Unsupported("WN in_layer shape");
             std::vector<int> gm(2 * H);  // interleave (tanh_j, sigmoid_j) so one thread owns a gate pair
             for (int j = 0; j < H; ++j) { gm[2 * j] = j; gm[2 * j + 1] = H + j; }
-            C.in.push_back(make_conv(in, gm));
+            C.in.push_back(make_conv(in, gm, {}, 1.f, -1, true, false, true));
             const ConvRec& rs = L.wn.res_skip[l];
             const bool last = l == L.wn.nLayers - 1;
             if (rs.inCh != H || rs.outCh != (last ? H : 2 * H) || rs.k != 1) throw Unsupported("WN res_skip shape");
-            C.rs.push_back(make_conv(rs));
+            C.rs.push_back(make_conv(rs, {}, {}, 1.f, -1, true, false, true));
         }
         if (L.wn.hasCond) {
             const ConvRec& cd = L.wn.cond;
@@ -1006,6 +1010,19 @@ void stts_engine::run() {
         for (auto& c : L.rs) flowTc = flowTc && tc_layer(c);
     }
     if (flowTc) { hP = arena_planes(Ft, B, WH); actsP = arena_planes(Ft, B, WH); skipP = arena_planes(Ft, B, WH); }
+    // WaveNet layers on the staged-epilogue wide conv (pc_fused.cuh): h and skip live as planes only
+    static const int env_pc = getenv("STTS_PC_FUSED") ? atoi(getenv("STTS_PC_FUSED")) : 1;
+    bool flowPc = flowTc && env_pc;
+    for (auto& L : flow) {
+        for (auto& c : L.in) flowPc = flowPc && pc_eligible(c.pc, PC_EPI_GATE) && c.Cout == 2 * WH && c.Cin == WH;
+        for (auto& c : L.rs) flowPc = flowPc && pc_eligible(c.pc, PC_EPI_RS) && c.Cin == WH;
+    }
+    const int2* ftiles = nullptr; int nftiles = 0;
+    if (flowPc) {
+        std::vector<int> lens(B);
+        for (int u = 0; u < B; ++u) lens[u] = h_foff[u + 1] - h_foff[u];
+        ftiles = rb_tiles(Seg{d_foff, 1, 0}, lens, 128, nftiles);
+    }
 #endif
 
     // ---- length regulator (expandM, SynthesizerTrn.cpp:304-321, :380-383) -----------------------
@@ -1030,6 +1047,7 @@ void stts_engine::run() {
 #ifdef STTS_WITH_TC
             if (flowTc) { po.out_planes = &hP; po.y_tt = true; }   // h feeds the k5 in-layer as planes; its fp32 copy is
                                                                    // only ever touched by the res_skip epilogues
+            if (flowPc) { po.y_tt = false; po.write_f32 = false; } // ... and not at all on the staged-epilogue path
 #endif
             conv(L.pre, x0, inter, hbuf, WH, fseg, B, maxF, po);                 // h = pre(x0)
         }
@@ -1047,6 +1065,25 @@ void stts_engine::run() {
                 r.y_tt = true; r.y2_tt = true;           // h / skip fp32: tile-transposed (coalesced read-modify-write)
                 if (l < nl - 1) r.out_planes = &hP;      // refreshed h for the next in-layer
                 else r.out2_planes = &skipP;             // finished skip sum feeds `post`
+            }
+#endif
+#ifdef STTS_WITH_TC
+            if (flowPc) {
+                const int pmode = tensor_mode == 2 ? 1 : 0;
+                ProfRec pr;
+                if (profOn) prof_begin(pr, 2.0 * L.in[l].macs_row * (double)curRowsTotal);
+                int rc = pc_launch(PC_EPI_GATE, L.in[l].pc, hP, actsP, actsP, 0, 0, 0, g.gvec, g.ldg, fseg, ftiles, nftiles, pmode, sms, d_flags, stream);
+                if (rc < 0) throw CudaError("WN in_layer launch failed (" + std::to_string(rc) + ")");
+                launch_check();
+                if (profOn) prof_end(pr);
+                curCls = STTS_CLS_WN_RS;
+                if (profOn) prof_begin(pr, 2.0 * L.rs[l].macs_row * (double)curRowsTotal);
+                rc = pc_launch(PC_EPI_RS, L.rs[l].pc, actsP, hP, skipP, (l < nl - 1) ? WH : 0, 1, l > 0 ? 1 : 0, nullptr, 0, fseg, ftiles, nftiles, pmode, sms,
+                               d_flags, stream);
+                if (rc < 0) throw CudaError("WN res_skip launch failed (" + std::to_string(rc) + ")");
+                launch_check();
+                if (profOn) prof_end(pr);
+                continue;
             }
 #endif
             conv(L.in[l], hbuf, WH, acts, WH, fseg, B, maxF, g);

@@ -105,15 +105,16 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* b, uint32_t parity) {
 }
 
 struct RbTile { int u, seg0, len, t0; long long prow_u; };
-__device__ __forceinline__ RbTile rb_tile(const RbP& p, int w) {
+__device__ __forceinline__ RbTile rb_tile_at(const Seg& seg, const int2* tiles, int w) {
     RbTile it;
-    const int2 e = __ldg(p.tiles + w);
+    const int2 e = __ldg(tiles + w);
     it.u = e.x; it.t0 = e.y;
-    it.len = seg_len(p.seg, e.x);
-    it.seg0 = seg_start(p.seg, e.x);
-    it.prow_u = planes_row(p.seg, e.x);
+    it.len = seg_len(seg, e.x);
+    it.seg0 = seg_start(seg, e.x);
+    it.prow_u = planes_row(seg, e.x);
     return it;
 }
+__device__ __forceinline__ RbTile rb_tile(const RbP& p, int w) { return rb_tile_at(p.seg, p.tiles, w); }
 // (utterance, first row) of every super-tile of `ov` rows, utterance-major; one block
 __global__ void __launch_bounds__(256) rb_tiles_kernel(Seg seg, int nseg, int ov, int2* __restrict__ out, int cap) {
     __shared__ int scan[256];
