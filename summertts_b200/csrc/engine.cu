@@ -1011,8 +1011,12 @@ void stts_engine::run() {
     }
     if (flowTc) { hP = arena_planes(Ft, B, WH); actsP = arena_planes(Ft, B, WH); skipP = arena_planes(Ft, B, WH); }
     // WaveNet layers on the staged-epilogue wide conv (pc_fused.cuh): h and skip live as planes only
-    static const int env_pc = getenv("STTS_PC_FUSED") ? atoi(getenv("STTS_PC_FUSED")) : 1;
-    bool flowPc = flowTc && env_pc;
+    // STTS_PC_FUSED bit 0: res_skip, bit 1: in_layer.  Measured (1xB200, 64 x 640 frames): res_skip 107 -> 74 us per launch on
+    // the staged-epilogue kernel; the k5 in_layer is bound by the depth of its weight ring there (64 KB beside a 101 KB activation
+    // tile: 195 us vs 142 us for conv_tc's column-split tiles), so by default it stays on conv_tc except in throughput mode.
+    static const int env_pc = getenv("STTS_PC_FUSED") ? atoi(getenv("STTS_PC_FUSED")) : -1;
+    const int pc_bits = env_pc >= 0 ? env_pc : (tensor_mode == 2 ? 3 : 1);
+    bool flowPc = flowTc && pc_bits != 0;
     for (auto& L : flow) {
         for (auto& c : L.in) flowPc = flowPc && pc_eligible(c.pc, PC_EPI_GATE) && c.Cout == 2 * WH && c.Cin == WH;
         for (auto& c : L.rs) flowPc = flowPc && pc_eligible(c.pc, PC_EPI_RS) && c.Cin == WH;
@@ -1071,12 +1075,16 @@ void stts_engine::run() {
             if (flowPc) {
                 const int pmode = tensor_mode == 2 ? 1 : 0;
                 ProfRec pr;
-                if (profOn) prof_begin(pr, 2.0 * L.in[l].macs_row * (double)curRowsTotal);
-                int rc = pc_launch(PC_EPI_GATE, L.in[l].pc, hP, actsP, actsP, 0, 0, 0, g.gvec, g.ldg, fseg, ftiles, nftiles, pmode, sms, d_flags, stream);
-                if (rc < 0) throw CudaError("WN in_layer launch failed (" + std::to_string(rc) + ")");
-                launch_check();
-                if (profOn) prof_end(pr);
+                int rc;
+                if (pc_bits & 2) {
+                    if (profOn) prof_begin(pr, 2.0 * L.in[l].macs_row * (double)curRowsTotal);
+                    rc = pc_launch(PC_EPI_GATE, L.in[l].pc, hP, actsP, actsP, 0, 0, 0, g.gvec, g.ldg, fseg, ftiles, nftiles, pmode, sms, d_flags, stream);
+                    if (rc < 0) throw CudaError("WN in_layer launch failed (" + std::to_string(rc) + ")");
+                    launch_check();
+                    if (profOn) prof_end(pr);
+                } else conv(L.in[l], hbuf, WH, acts, WH, fseg, B, maxF, g);      // conv_tc: hP planes -> gate -> actsP planes
                 curCls = STTS_CLS_WN_RS;
+                if (!(pc_bits & 1)) throw std::runtime_error("STTS_PC_FUSED: the in_layer alone cannot run on the staged-epilogue path");
                 if (profOn) prof_begin(pr, 2.0 * L.rs[l].macs_row * (double)curRowsTotal);
                 rc = pc_launch(PC_EPI_RS, L.rs[l].pc, actsP, hP, skipP, (l < nl - 1) ? WH : 0, 1, l > 0 ? 1 : 0, nullptr, 0, fseg, ftiles, nftiles, pmode, sms,
                                d_flags, stream);

@@ -47,7 +47,22 @@ struct PcP {
     int split;                       // RS: first chunk that belongs to out1
     int acc0, acc1;                  // RS: add the stream's previous value (0: store the conv result alone)
     unsigned int* flags;
+    int ncta;                        // CTAs per cluster (1 or 2): with 2, each CTA fetches HALF of every weight stage and multicasts it to both
+                                     // (the two CTAs work on the same chunk pair of two different row tiles), halving the L2 -> SM weight traffic
+    int nclu_items;                  // cluster work items: npairs * ceil(ntiles / ncta)
 };
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 
 // element (row r, group g) of a staging tile [planes][groups][128 rows][16 B]
 __device__ __forceinline__ uint8_t* pc_cell(uint8_t* stg, int groups, int plane, int g, int r) {
@@ -74,10 +89,22 @@ __device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const ui
     const int kcs = p.G / 8;                                        // 64-channel blocks per tap
     uint32_t af_par = 0, e_par = 1;
     int bs = 0; uint32_t bph = 0;
-    const int W = p.work_items, step = gridDim.x;
-    for (int w = blockIdx.x; w < W; w += step) {
-        const int pair = w % p.npairs;
-        const bool active = pair * 2 + slot < p.nchunks;
+    const int W = p.nclu_items, step = gridDim.x / p.ncta;
+    const int rank = p.ncta == 2 ? (int)cluster_rank() : 0;
+    const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
+    for (int w = blockIdx.x / p.ncta; w < W; w += step) {
+        const int pair = w % p.npairs, ti = (w / p.npairs) * p.ncta + rank;
+        const bool active = pair * 2 + slot < p.nchunks && ti < p.ntiles;
+        if (ti >= p.ntiles) {                      // a cluster's odd tail: no tile for this CTA, only the weight-stage protocol runs
+            for (int s = 0; s < 2 * p.nst; ++s) {
+                const int slot_r = bs; const uint32_t ph_r = bph;
+                if (++bs == p.nb) { bs = 0; bph ^= 1; }
+                if ((s & 1) != slot) continue;
+                mbar_wait(&b_full[slot_r], ph_r);
+                if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
+            }
+            continue;
+        }
         mbar_wait(a_full, af_par); af_par ^= 1;
         tc_fence_after();
         const int nst = p.nst;
@@ -96,7 +123,11 @@ __device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const ui
                     const int slot_r = bs; const uint32_t ph_r = bph;
                     if (++bs == p.nb) { bs = 0; bph ^= 1; }
                     if (q != slot) continue;
-                    if (mode && ((s & 1) != KIND)) { mbar_wait(&b_full[slot_r], ph_r); tc_commit(&b_empty[slot_r]); continue; }   // not this issuer's stage: just release it
+                    if (mode && ((s & 1) != KIND)) {          // not this issuer's stage: just release it
+                        mbar_wait(&b_full[slot_r], ph_r);
+                        if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
+                        continue;
+                    }
                     mbar_wait(&b_full[slot_r], ph_r);
                     tc_fence_after();
                     if (active) {
@@ -107,7 +138,7 @@ __device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const ui
                         for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_t, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc, ks == 0 ? acc : 1u);
                         acc = 1u;
                     }
-                    tc_commit(&b_empty[slot_r]);
+                    if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
                 }
             }
             s_done = s1;
@@ -149,7 +180,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
             mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 8);
             mbar_init(&r_full[i], 1); mbar_init(&s_free[i], 1);
         }
-        for (int s = 0; s < PC_MAX_RING; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2); }
+        for (int s = 0; s < PC_MAX_RING; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2 * p.ncta); }    // both issuers of the slot, in every CTA of the cluster
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) {
@@ -161,7 +192,9 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;     // slot s: main @ s*192 (128 columns: hi*hi | hi*lo), corr @ s*192 + 128 (64 columns)
-    const int W = p.work_items, wstep = gridDim.x;
+    if (p.ncta == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
+    const int W = p.nclu_items, wstep = gridDim.x / p.ncta;
+    const int crank = p.ncta == 2 ? (int)cluster_rank() : 0;
 
     if (warp < 16) {
         // ================= promotion + epilogue: (slot, column half hf), one row x 32 columns per thread ==================
@@ -176,10 +209,10 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
         const int SPU = p.mode ? (1 << 20) : max(1, p.usteps / 4);
         const int NU = p.mode ? 1 : (p.nst + SPU - 1) / SPU;
         int item = 0;
-        for (int w = blockIdx.x; w < W; w += wstep, ++item) {
-            const int pair = w % p.npairs, ti = w / p.npairs;
+        for (int w = blockIdx.x / p.ncta; w < W; w += wstep, ++item) {
+            const int pair = w % p.npairs, ti = (w / p.npairs) * p.ncta + crank;
             const int chunk = pair * 2 + slot;
-            const bool active = chunk < p.nchunks;
+            const bool active = chunk < p.nchunks && ti < p.ntiles;
             if (!active) continue;                    // (the partner slot still runs; nothing of this slot's barriers is used)
             const RbTile it = rb_tile_at(p.seg, p.tiles, ti);
             for (int un = 0; un < NU; ++un) {
@@ -321,15 +354,17 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
     } else {
         // ================= producer: activation tiles, residual tiles (RS) and weight stages, one thread, cooperative polling ===
         if (lane == 0) {
-            int xw = blockIdx.x; uint32_t ae_par = 1;
-            int rw = blockIdx.x; uint32_t sf_par0 = 1, sf_par1 = 1; int rslot = 0;
-            int ww = blockIdx.x, wstage = 0, wq2 = 0, ws_ = 0; uint32_t wph = 1;
+            int xw = blockIdx.x / p.ncta; uint32_t ae_par = 1;
+            int rw = blockIdx.x / p.ncta; uint32_t sf_par0 = 1, sf_par1 = 1; int rslot = 0;
+            int ww = blockIdx.x / p.ncta, wstage = 0, wq2 = 0, ws_ = 0; uint32_t wph = 1;
+            const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
             if (EPI != PC_EPI_RS) rw = W;
             while (xw < W || ww < W || rw < W) {
                 bool progress = false;
-                if (xw < W && mbar_test(a_empty, ae_par)) {
+                if (xw < W && (xw / p.npairs) * p.ncta + crank >= p.ntiles) { xw += wstep; progress = true; }      // odd tail: no tile for this CTA
+                else if (xw < W && mbar_test(a_empty, ae_par)) {
                     ae_par ^= 1;
-                    const RbTile it = rb_tile_at(p.seg, p.tiles, xw / p.npairs);
+                    const RbTile it = rb_tile_at(p.seg, p.tiles, (xw / p.npairs) * p.ncta + crank);
                     const long long r0 = it.prow_u + it.t0 - p.padl;
                     mbar_expect_tx(a_full, a_tile);
                     tma_load_3d(abuf, &imap, 0, (int)r0, 0, a_full);
@@ -339,7 +374,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                 if (rw < W) {                          // residual tile of (item rw, slot rslot): hi groups, then lo groups
                     const int chunk = (rw % p.npairs) * 2 + rslot;
                     const bool to1 = chunk >= p.split;
-                    const bool act = chunk < p.nchunks;
+                    const int rti = (rw / p.npairs) * p.ncta + crank;
+                    const bool act = chunk < p.nchunks && rti < p.ntiles;
                     const bool need = act && (to1 ? p.acc1 != 0 : p.acc0 != 0);
                     bool adv = !act;
                     // every active chunk's epilogue frees the staging tile once (s_free); the producer consumes each of those
@@ -350,7 +386,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                         progress = true;
                     }
                     if (act && adv && need) {
-                        const RbTile it = rb_tile_at(p.seg, p.tiles, rw / p.npairs);
+                        const RbTile it = rb_tile_at(p.seg, p.tiles, rti);
                         const Planes& op = to1 ? p.out1 : p.out0;
                         const int oc = to1 ? chunk - p.split : chunk;
                         const CUtensorMap* rm = to1 ? &rmap1 : &rmap0;
@@ -367,7 +403,10 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                     const int cc = min(chunk, p.nchunks - 1);          // an inactive slot still gets (ignored) bytes: keeps the ring walk uniform
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + ((size_t)cc * p.nst + wstage) * PC_STAGE;
                     mbar_expect_tx(&b_full[ws_], PC_STAGE);
-                    bulk_g2s(wst + (size_t)ws_ * PC_STAGE, src, PC_STAGE, &b_full[ws_]);
+                    if (p.ncta == 2) {        // this CTA fetches its half of the stage and multicasts it into both CTAs (same offsets, same barrier)
+                        const uint32_t half = PC_STAGE / 2;
+                        bulk_g2s_mc(wst + (size_t)ws_ * PC_STAGE + crank * half, src + crank * half, half, &b_full[ws_], mc_mask);
+                    } else bulk_g2s(wst + (size_t)ws_ * PC_STAGE, src, PC_STAGE, &b_full[ws_]);
                     if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
                     if (++wq2 == 2) { wq2 = 0; if (++wstage == p.nst) { wstage = 0; ww += wstep; } }
                     progress = true;
@@ -378,6 +417,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
         __syncwarp();
     }
     __syncthreads();
+    if (p.ncta == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 16) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -488,15 +528,38 @@ inline int pc_launch(int epi, const PcWeights& w, const Planes& in, const Planes
     if (!pc_make_map(&imap, in, p.xr, 2 * p.G)) return -1;
     const Planes& r0 = (epi == PC_EPI_RS && split_ch > 0) ? out0 : out1;
     if (!pc_make_map(&rmap0, epi == PC_EPI_RS ? r0 : in, 128, 8) || !pc_make_map(&rmap1, epi == PC_EPI_RS ? out1 : in, 128, 8)) return -1;
-    int ctas = std::min(sms, p.work_items);
+    static const int env_clu = getenv("STTS_PC_CLUSTER") ? atoi(getenv("STTS_PC_CLUSTER")) : 1;   // 2: weight multicast in CTA pairs (works; measured no gain: the ring depth, not L2 bandwidth, bounds these kernels)
+    p.ncta = (env_clu == 2 && ntiles >= 2) ? 2 : 1;
+    p.nclu_items = p.npairs * ((ntiles + p.ncta - 1) / p.ncta);
+    int ctas = std::min(sms, p.nclu_items * p.ncta);
+    ctas -= ctas % p.ncta;
     static const int env_verbose = getenv("STTS_TC_VERBOSE") ? atoi(getenv("STTS_TC_VERBOSE")) : 0;
     if (env_verbose > 0) {
         static int left = 8;
         if (left > 0) { --left; fprintf(stderr, "pc_conv: epi=%d Cin=%d Cout=%d k=%d mode=%d items=%d ctas=%d smem=%zu nb=%d nst=%d\n", epi, w.Cin, w.Cout, w.k, mode, p.work_items, ctas, pl.smem, pl.nb, w.nst); }
     }
-    if (epi == PC_EPI_GATE) pc_kernel<PC_EPI_GATE><<<ctas, PC_THREADS, pl.smem, stream>>>(p, imap, rmap0, rmap1);
-    else pc_kernel<PC_EPI_RS><<<ctas, PC_THREADS, pl.smem, stream>>>(p, imap, rmap0, rmap1);
-    return 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(PC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (p.ncta == 2) {
+        // persistent CTAs walk the items with a static stride: every cluster must be resident at once, or the late ones
+        // serialise behind a whole pass of the others.  GPCs with an odd SM count leave some SMs without a partner.
+        int maxc = 0;
+        const cudaError_t oe = epi == PC_EPI_GATE ? cudaOccupancyMaxActiveClusters(&maxc, pc_kernel<PC_EPI_GATE>, &cfg)
+                                                 : cudaOccupancyMaxActiveClusters(&maxc, pc_kernel<PC_EPI_RS>, &cfg);
+        if (oe == cudaSuccess && maxc > 0 && 2 * maxc < ctas) { ctas = 2 * maxc; cfg.gridDim = dim3(ctas); }
+    }
+    if (env_verbose > 0) {
+        static int left2 = 4;
+        if (left2 > 0) { --left2; fprintf(stderr, "pc_conv: cluster %d, grid %d, cluster items %d\n", p.ncta, ctas, p.nclu_items); }
+    }
+    cudaError_t le;
+    if (epi == PC_EPI_GATE) le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_GATE>, p, imap, rmap0, rmap1);
+    else le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_RS>, p, imap, rmap0, rmap1);
+    return le == cudaSuccess ? 1 : -5;
 }
 
 }  // namespace stts
