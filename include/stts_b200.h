@@ -93,6 +93,15 @@ int stts_batch_fetch(stts_engine* e, int16_t* pcm_out, int64_t cap_samples, int6
  * over the batch); NULL clears.  Used for shape-stable benches and downstream-stage parity. */
 int stts_set_forced_durations(stts_engine* e, const float* w_ceil, int64_t n);
 
+/* Chunked / streaming synthesis of one utterance (the reference feeds whole files as one utterance and returns
+ * only at the end, test/main.cpp:90-142).  The token-level half (text encoder, duration predictor, length regulator) runs once;
+ * flow + decoder then run over chunks of `chunk_frames` frames with a halo covering their receptive field, and `cb` receives each
+ * chunk's PCM (a host buffer valid during the call) in order.  The concatenation is bit-identical to stts_infer_ids.
+ * *first_chunk_ms: GPU time from the start of the call to the first chunk's PCM on the host. */
+typedef void (*stts_pcm_callback)(const int16_t* pcm, int64_t n, void* user);
+int stts_infer_stream(stts_engine* e, const int32_t* ids, int32_t n, int32_t sid, float length_scale, int32_t chunk_frames,
+                      stts_pcm_callback cb, void* user, float* first_chunk_ms, int64_t* total_samples);
+
 /* Stage tensors of utterance 0 of the last run, time-major [rows][cols] float32.
  * which: 0 xx[T][hidden]  1 m[T][inter]  2 logw[T]  3 w_ceil[T]  4 z_p[F][inter]  5 z[F][inter]
  *        6 o[S] (raw float waveform).  Returns a malloc'd buffer in *out (stts_free). */

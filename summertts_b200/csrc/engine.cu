@@ -197,6 +197,14 @@ struct stts_engine {
     std::vector<int64_t> h_soff;
     int16_t* d_pcm = nullptr;
     bool runValid = false;       // the last run() completed: d_pcm / dbg / h_soff describe it
+    // chunked / streaming synthesis (stts_infer_stream): run() either stops after the length regulator and keeps z_p
+    // (stopAfterRegulate), or skips the token-level half and runs flow + decoder on an injected slice of it (injectZ)
+    const float* injectZ = nullptr;
+    int injectF = 0;
+    bool stopAfterRegulate = false;
+    float* streamZ = nullptr;
+    size_t streamZCap = 0;
+    int streamF = 0;
     struct Dbg {
         float *xx = nullptr, *m = nullptr, *logw = nullptr, *wceil = nullptr, *zp = nullptr, *z = nullptr, *o = nullptr;
     } dbg;
@@ -856,6 +864,7 @@ void stts_engine::run() {
             if (gWn[i]) conv(flow[i].cond, G, gin, gWn[i], flow[i].cond.Cout, bseg, 1, B, o);
     }
 
+    if (!injectZ) {
     // ---- text encoder (TextEncoder.cpp:50-74, attention_encoder.cpp:78-94) ---------------------
     curCls = STTS_CLS_ENC; curRowsTotal = Tt;
     embed_kernel<<<((size_t)Tt * H + 255) / 256, 256, 0, stream>>>(d_ids, emb, x, Tt, H, vocab, std::sqrt((float)H));
@@ -944,8 +953,13 @@ void stts_engine::run() {
     }
     CUDA_CHECK(cudaMemcpyAsync(hostInts, d_nfr, (size_t)B * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));  // frame counts size every grid below (SynthesizerTrn.cpp:376-378)
+    }   // !injectZ
     h_foff.assign(B + 1, 0);
     maxF = 0;
+    if (injectZ) {
+        if (B != 1 || injectF <= 0) throw ArgError("chunk injection needs a single staged utterance");
+        h_foff[1] = injectF; maxF = injectF;
+    } else
     for (int u = 0; u < B; ++u) {
         h_foff[u + 1] = h_foff[u] + hostInts[u];
         maxF = std::max(maxF, hostInts[u]);
@@ -1030,13 +1044,26 @@ void stts_engine::run() {
 #endif
 
     // ---- length regulator (expandM, SynthesizerTrn.cpp:304-321, :380-383) -----------------------
-    {
+    if (injectZ) CUDA_CHECK(cudaMemcpyAsync(z, injectZ, (size_t)Ft * inter * 4, cudaMemcpyDeviceToDevice, stream));
+    else {
         dim3 g((maxF + 3) / 4, B);
         regulate_kernel<<<g, 128, 0, stream>>>(mbuf, inter, tokFirst, wceil, d_toff, d_foff, z, inter);
         launch_check();
         if (debug) CUDA_CHECK(cudaMemcpyAsync(zp_dbg, z, (size_t)Ft * inter * 4, cudaMemcpyDeviceToDevice, stream));
     }
     CUDA_CHECK(cudaEventRecord(ev[3], stream));
+    if (stopAfterRegulate) {      // keep z_p for the chunked flow + decoder passes
+        const size_t nb = (size_t)Ft * inter * 4;
+        if (nb > streamZCap) {
+            if (streamZ) { float* old = streamZ; streamZ = nullptr; CUDA_CHECK(cudaFree(old)); }
+            CUDA_CHECK(cudaMalloc((void**)&streamZ, nb + nb / 4));
+            streamZCap = nb + nb / 4;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(streamZ, z, nb, cudaMemcpyDeviceToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        streamF = Ft;
+        return;
+    }
 
     // ---- flow: ResidualCouplingBlock::forward (reverse), ResidualCouplingBlock.cpp:59-71 --------
     const int half = inter / 2;
@@ -1308,7 +1335,8 @@ void stts_engine::run() {
     const int sMul = R * tailMul;
     h_soff.assign(B + 1, 0);
     for (int u = 0; u <= B; ++u) h_soff[u] = (int64_t)h_foff[u] * sMul;
-    dbg.xx = x; dbg.m = mbuf; dbg.logw = logw; dbg.wceil = wceil; dbg.zp = zp_dbg; dbg.z = z; dbg.o = o;
+    if (!injectZ) { dbg.xx = x; dbg.m = mbuf; dbg.logw = logw; dbg.wceil = wceil; dbg.zp = zp_dbg; }
+    dbg.z = z; dbg.o = o;
     runValid = true;
 }
 
@@ -1387,6 +1415,7 @@ void stts_destroy(stts_engine* e) {
     if (e->planeScratch) cudaFree(e->planeScratch);
 #endif
     if (e->wsAlloc) cudaFree(e->wsAlloc);
+    if (e->streamZ) cudaFree(e->streamZ);
     for (void* p : {(void*)e->d_ids, (void*)e->d_toff, (void*)e->d_sids, (void*)e->d_ls, (void*)e->d_foff, (void*)e->d_nfr,
                     (void*)e->d_bseg, (void*)e->d_forced})
         if (p) cudaFree(p);
@@ -1496,6 +1525,75 @@ int stts_infer_batch(stts_engine* e, int32_t B, const int32_t* ids, const int32_
             ns[u] = (int32_t)n;
         }
     });
+}
+
+// Chunked synthesis of one utterance: the token-level half runs once, then flow + decoder run over
+// frame chunks with a halo that covers their receptive field; every chunk's PCM is handed to `cb` as soon as it is on the
+// host.  The flow and the decoder are purely convolutional (ResidualCouplingBlock.cpp:59-71, Generator_MS.cpp:166-229), so the
+// concatenated chunks are bit-identical to the one-shot result.  The reference synthesises the whole text as one utterance
+// and returns only at the end (test/main.cpp:90-142).
+int stts_infer_stream(stts_engine* e, const int32_t* ids, int32_t n, int32_t sid, float ls, int32_t chunk_frames,
+                      stts_pcm_callback cb, void* user, float* first_chunk_ms, int64_t* total_samples) {
+    int rc = guard([&] {
+        if (!e || !ids || !cb || chunk_frames < 16) throw ArgError("null argument or chunk_frames < 16");
+        CUDA_CHECK(cudaSetDevice(e->device));
+        cudaEvent_t t0, t1;
+        CUDA_CHECK(cudaEventCreate(&t0)); CUDA_CHECK(cudaEventCreate(&t1));
+        CUDA_CHECK(cudaEventRecord(t0, e->stream));
+        const int32_t offs[2] = {0, n};
+        e->stage(1, ids, offs, &sid, &ls);
+        e->injectZ = nullptr; e->stopAfterRegulate = true;
+        try { e->run(); } catch (...) { e->stopAfterRegulate = false; throw; }
+        e->stopAfterRegulate = false;
+        const int F = e->streamF;
+        // receptive-field halo in frames: flow = sum over coupling layers / WN layers of (k-1)/2; decoder = conv_pre + per stage
+        // (transposed conv taps + the deepest ResBlock1 branch) / rate + the tail (subband conv, iSTFT overlap, synthesis FIR)
+        int halo = 0;
+        for (auto& L : e->flow) for (auto& c : L.in) halo += (c.k - 1) / 2 * c.dil;
+        halo += e->convPre.padl + 1;
+        int rate = 1;
+        for (size_t s = 0; s < e->ups.size(); ++s) {
+            halo += (e->ups[s].k + rate - 1) / rate + 1;
+            rate *= e->upRates[s];
+            int deepest = 0;
+            for (int j = 0; j < e->nRbK; ++j) {
+                int rows = 0;
+                const auto& rb = e->rbs[s * e->nRbK + j];
+                for (size_t q = 0; q < rb.c1.size(); ++q) rows += rb.c1[q].padl + rb.c2[q].padl;
+                deepest = std::max(deepest, rows);
+            }
+            halo += (deepest + rate - 1) / rate + 1;
+        }
+        halo += 4;
+        int64_t total = 0;
+        bool first = true;
+        const int sMul = [&] { int R = 1; for (int r : e->upRates) R *= r; return R * (e->decType == 0 ? 1 : (e->decType == 2 ? 4 : 16)); }();
+        for (int c0 = 0; c0 < F; c0 += chunk_frames) {
+            const int c1 = std::min(F, c0 + chunk_frames);
+            const int s0 = std::max(0, c0 - halo), s1 = std::min(F, c1 + halo);
+            e->injectZ = e->streamZ + (size_t)s0 * e->inter; e->injectF = s1 - s0;
+            try { e->run(); } catch (...) { e->injectZ = nullptr; throw; }
+            e->injectZ = nullptr;
+            const int64_t ns = (int64_t)(c1 - c0) * sMul, off = (int64_t)(c0 - s0) * sMul;
+            if ((size_t)ns > e->hostPcmCap) {
+                if (e->hostPcm) CUDA_CHECK(cudaFreeHost(e->hostPcm));
+                e->hostPcm = nullptr; e->hostPcmCap = 0;
+                CUDA_CHECK(cudaMallocHost((void**)&e->hostPcm, (size_t)ns * 2 + 4096));
+                e->hostPcmCap = (size_t)ns + 2048;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(e->hostPcm, e->d_pcm + off, (size_t)ns * 2, cudaMemcpyDeviceToHost, e->stream));
+            if (first) CUDA_CHECK(cudaEventRecord(t1, e->stream));
+            CUDA_CHECK(cudaStreamSynchronize(e->stream));
+            if (first && first_chunk_ms) CUDA_CHECK(cudaEventElapsedTime(first_chunk_ms, t0, t1));
+            first = false;
+            cb(e->hostPcm, ns, user);
+            total += ns;
+        }
+        if (total_samples) *total_samples = total;
+        e->runValid = false;          // d_pcm holds only the last chunk
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+    });
+    return rc;
 }
 
 int stts_infer_ids(stts_engine* e, const int32_t* ids, int32_t n, int32_t sid, float ls, int16_t** pcm, int32_t* ns) {

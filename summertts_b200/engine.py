@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
-    "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks",
+    "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks", "stts_infer_stream",
 ]
 
 _lib = None
@@ -224,6 +224,24 @@ class SynthesizerTrn:
 
     def kernel_launches(self) -> int:
         return int(self._L.stts_kernel_launches(self._h))
+
+    def infer_stream(self, ids, sid=0, length_scale=1.0, chunk_frames=128):
+        """Chunked synthesis: returns (list of per-chunk int16 arrays in emission order, GPU ms to the first chunk)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        chunks = []
+        CB = C.CFUNCTYPE(None, C.POINTER(C.c_int16), C.c_int64, C.c_void_p)
+
+        def on_pcm(ptr, n, _user):
+            chunks.append(np.ctypeslib.as_array(ptr, shape=(n,)).copy())
+
+        cb = CB(on_pcm)
+        first, total = C.c_float(0), C.c_int64(0)
+        self._L.stts_infer_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, CB, C.c_void_p,
+                                              C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+        _check(self._L.stts_infer_stream(self._h, ids.ctypes.data, ids.size, int(sid), float(length_scale), int(chunk_frames), cb, None,
+                                         C.byref(first), C.byref(total)))
+        assert total.value == sum(c.size for c in chunks)
+        return chunks, float(first.value)
 
     def tensor_fallbacks(self) -> int:
         """Batches recomputed on the fp32 FFMA tiles because an activation left the split-fp16 range."""
