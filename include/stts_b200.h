@@ -93,6 +93,13 @@ int stts_batch_fetch(stts_engine* e, int16_t* pcm_out, int64_t cap_samples, int6
  * over the batch); NULL clears.  Used for shape-stable benches and downstream-stage parity. */
 int stts_set_forced_durations(stts_engine* e, const float* w_ceil, int64_t n);
 
+/* stts_create with a pre-packed device image on disk (the reference re-parses and copies every weight at every
+ * process start, SynthesizerTrn.cpp:91-167 + utils.cpp:8-32).  A missing / stale / foreign image is ignored and rewritten; a
+ * matching one (keyed by a hash of the NN section and the library version) supplies every dense conv's packed device representation.
+ * *from_image = 1 when the image was used.  image_path NULL or "" = stts_create. */
+int stts_create_cached(const float* model_blob, int64_t model_bytes, int device, const char* image_path, stts_engine** out,
+                       int32_t* from_image);
+
 /* Chunked / streaming synthesis of one utterance (the reference feeds whole files as one utterance and returns
  * only at the end, test/main.cpp:90-142).  The token-level half (text encoder, duration predictor, length regulator) runs once;
  * flow + decoder then run over chunks of `chunk_frames` frames with a halo covering their receptive field, and `cb` receives each

@@ -284,11 +284,75 @@ struct stts_engine {
 
     int tc_usteps = 4;   // promotion unit (MMA steps) for the layers built next: 4 for token-level layers, 8 from the flow on
 
+    // ---- pre-packed device image ------------------------------------------------------------------------
+    // Every dense conv's device-side representation (fp32 [k][Cin][CoutW], bias, and the packed split-fp16 stages of the three
+    // tensor-core kernels) is a DConv + up to five blobs.  In record mode build() appends them to a file in creation order; in
+    // replay mode make_conv & co. read the next record instead of transposing / splitting / packing on the host.  The file is
+    // keyed by a hash of the NN section, the library version and sizeof(DConv).
+    struct Image { int mode = 0; FILE* f = nullptr; int64_t nrec = 0; } img;      // mode 1 record, 2 replay
+#ifdef STTS_WITH_TC
+    static size_t tc_packed_bytes(const TcWeights& t) { return t.ok ? (size_t)t.nchunks * t.kchunks * t.taps * 2 * t.KC * t.NC * 2 : 0; }
+#endif
+    void img_put(const void* p, size_t n) { if (fwrite(p, 1, n, img.f) != n) throw std::runtime_error("device image: write failed"); }
+    void img_get(void* p, size_t n) { if (fread(p, 1, n, img.f) != n) throw FormatError("device image: truncated"); }
+    void img_put_blob(const void* dev, size_t n) {
+        const uint64_t n64 = n;
+        img_put(&n64, 8);
+        if (!n) return;
+        std::vector<char> h(n);
+        CUDA_CHECK(cudaMemcpy(h.data(), dev, n, cudaMemcpyDeviceToHost));
+        img_put(h.data(), n);
+    }
+    void* img_get_blob(size_t expect) {
+        uint64_t n64 = 0;
+        img_get(&n64, 8);
+        if (n64 != expect) throw FormatError("device image: blob size mismatch");
+        if (!n64) return nullptr;
+        std::vector<char> h(n64);
+        img_get(h.data(), n64);
+        void* d = nullptr;
+        CUDA_CHECK(cudaMalloc(&d, n64));
+        owned.push_back(d);
+        CUDA_CHECK(cudaMemcpy(d, h.data(), n64, cudaMemcpyHostToDevice));
+        return d;
+    }
+    void img_record(const DConv& d) {
+        if (img.mode != 1) return;
+        img_put(&d, sizeof(DConv));
+        img_put_blob(d.w, (size_t)d.k * d.Cin * d.CoutW * 4);
+        img_put_blob(d.b, d.b ? (size_t)d.Cout * 4 : 0);
+#ifdef STTS_WITH_TC
+        img_put_blob(d.tc.packed, tc_packed_bytes(d.tc));
+        img_put_blob(d.rb.packed, d.rb.ok ? (size_t)d.rb.k * 4 * d.Cin * d.Cin : 0);
+        img_put_blob(d.pc.packed, d.pc.ok ? (size_t)d.pc.nchunks * d.pc.nst * PC_STAGE : 0);
+#endif
+        ++img.nrec;
+    }
+    // replay: the next record must describe a conv of the expected shape (a stale or foreign image is rejected, not trusted)
+    DConv img_replay(int k, int Cin, int Cout) {
+        DConv d;
+        img_get(&d, sizeof(DConv));
+        if (d.k != k || d.Cin != Cin || d.Cout != Cout) throw FormatError("device image: record does not match the model");
+        d.w = (float*)img_get_blob((size_t)d.k * d.Cin * d.CoutW * 4);
+        const bool hadb = d.b != nullptr;
+        d.b = (float*)img_get_blob(hadb ? (size_t)d.Cout * 4 : 0);
+#ifdef STTS_WITH_TC
+        d.tc.packed = (__half*)img_get_blob(tc_packed_bytes(d.tc));
+        d.rb.packed = (__half*)img_get_blob(d.rb.ok ? (size_t)d.rb.k * 4 * d.Cin * d.Cin : 0);
+        d.rb.bias = d.b;
+        d.pc.packed = (__half*)img_get_blob(d.pc.ok ? (size_t)d.pc.nchunks * d.pc.nst * PC_STAGE : 0);
+        d.pc.bias = d.b;
+#endif
+        ++img.nrec;
+        return d;
+    }
+
     // Build a dense conv in device layout [k][Cin'][CoutW'] from a file record W[o][k][c].
     // omap[new_o] = orig_o, cmap[new_c] = orig_c (identity when empty); sign scales w and b.
     DConv make_conv(const ConvRec& r, const std::vector<int>& omap = {}, const std::vector<int>& cmap = {},
                     float sign = 1.f, int padl = -1, bool tc_ok = true, bool rb_pair = false, bool pc_wide = false) {
         if (r.sep) throw Unsupported("depthwise record passed to dense conv builder");
+        if (img.mode == 2) return img_replay(r.k, cmap.empty() ? r.inCh : (int)cmap.size(), omap.empty() ? r.outCh : (int)omap.size());
         DConv d;
         d.Cout = omap.empty() ? r.outCh : (int)omap.size();
         d.Cin = cmap.empty() ? r.inCh : (int)cmap.size();
@@ -320,6 +384,7 @@ struct stts_engine {
 #else
         (void)tc_ok; (void)rb_pair; (void)pc_wide;
 #endif
+        img_record(d);
         return d;
     }
 
@@ -331,6 +396,12 @@ struct stts_engine {
         const int s = r.stride, p = r.pad, k = r.k;
         if (r.dil != 1) throw Unsupported("ConvTranspose1d with dilation != 1");
         if (k - 2 * p != s) throw Unsupported("ConvTranspose1d with k - 2*pad != stride");
+        if (img.mode == 2) {
+            int lo = 1 << 30, hi = -(1 << 30);
+            for (int ph = 0; ph < s; ++ph)
+                for (int kk = (ph + p) % s; kk < k; kk += s) { lo = std::min(lo, (ph + p - kk) / s); hi = std::max(hi, (ph + p - kk) / s); }
+            return img_replay(hi - lo + 1, r.inCh, s * r.outCh);
+        }
         int dmin = 1 << 30, dmax = -(1 << 30);
         for (int ph = 0; ph < s; ++ph)
             for (int kk = (ph + p) % s; kk < k; kk += s) {
@@ -359,6 +430,7 @@ struct stts_engine {
 #ifdef STTS_WITH_TC
         tc_prepare_weights(d.tc, w.data(), d.k, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
 #endif
+        img_record(d);
         return d;
     }
     DLN make_ln(const LNormRec& r) {
@@ -559,7 +631,8 @@ void stts_engine::build(const Model& M) {
             if (c->k != 1 || c->inCh != hidden || c->outCh != hidden) throw Unsupported("attention projections must be 1x1");
         EncL L;
         // fused q|k|v projection: one GEMM with N = 3*hidden
-        {
+        if (img.mode == 2) L.qkv = img_replay(1, hidden, 3 * hidden);
+        else {
             DConv d;
             d.Cin = hidden; d.Cout = 3 * hidden; d.CoutW = d.Cout; d.k = 1; d.dil = 1; d.padl = 0;
             std::vector<float> w((size_t)hidden * d.CoutW), b(d.Cout, 0.f);
@@ -574,6 +647,7 @@ void stts_engine::build(const Model& M) {
 #ifdef STTS_WITH_TC
             tc_prepare_weights(d.tc, w.data(), 1, d.Cin, d.Cout, d.CoutW, owned, tc_usteps);
 #endif
+            img_record(d);
             L.qkv = d;
         }
         L.o = make_conv(m.o);
@@ -1403,6 +1477,77 @@ int stts_create(const float* blob, int64_t bytes, int device, stts_engine** out)
         *out = e;
     });
     if (rc != STTS_OK && e) { stts_destroy(e); }
+    return rc;
+}
+
+// stts_create with a pre-packed device image on disk (the reference re-parses and copies every weight at
+// every process start, SynthesizerTrn.cpp:91-167 + utils.cpp:8-32).  image_path missing / stale / foreign: the engine is built
+// from the blob as usual and the image is (re)written; matching: every dense conv's packed device representation is read from the
+// image instead of being transposed, split and packed on the host.  *from_image = 1 when the image was used.
+static uint64_t nn_hash(const float* blob, int64_t nfloats) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(blob);
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)nfloats;
+    for (int64_t i = 0; i < nfloats; ++i) { h ^= w[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+    return h;
+}
+int stts_create_cached(const float* blob, int64_t bytes, int device, const char* image_path, stts_engine** out, int32_t* from_image) {
+    if (out) *out = nullptr;
+    if (from_image) *from_image = 0;
+    if (!image_path || !*image_path) return stts_create(blob, bytes, device, out);
+    stts_engine* e = nullptr;
+    int rc = guard([&] {
+        if (!blob || bytes < 16 || !out) throw ArgError("null blob / out");
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev <= 0)
+            throw CudaError(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(ce));
+        if (device < 0 || device >= ndev) throw ArgError("device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        Model M = parse_model(blob, bytes / 4);
+        struct Hdr { char magic[8]; uint64_t key; uint64_t dconv; int64_t nrec; } want;
+        memcpy(want.magic, "STTSIMG2", 8);
+        want.key = nn_hash(blob, M.nnEnd) ^ std::hash<std::string>()(stts_version());
+        want.dconv = sizeof(DConv);
+        want.nrec = 0;
+        for (int attempt = 0; attempt < 2 && !e; ++attempt) {
+            e = new stts_engine();
+            e->device = device;
+            CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+            for (auto& ev : e->ev) CUDA_CHECK(cudaEventCreate(&ev));
+            FILE* f = attempt == 0 ? fopen(image_path, "rb") : nullptr;
+            Hdr got;
+            if (f && fread(&got, sizeof(got), 1, f) == 1 && !memcmp(got.magic, want.magic, 8) && got.key == want.key && got.dconv == want.dconv) {
+                e->img.mode = 2; e->img.f = f;
+                try {
+                    e->build(M);
+                    if (e->img.nrec != got.nrec) throw FormatError("device image: record count mismatch");
+                    fclose(f); e->img.f = nullptr; e->img.mode = 0;
+                    if (from_image) *from_image = 1;
+                } catch (const FormatError&) {        // stale / truncated image: rebuild from the blob and rewrite it
+                    fclose(f); e->img.f = nullptr;
+                    stts_destroy(e); e = nullptr;
+                }
+            } else {
+                if (f) fclose(f);
+                const std::string tmp = std::string(image_path) + ".tmp";
+                FILE* w = fopen(tmp.c_str(), "wb");
+                if (w) { e->img.mode = 1; e->img.f = w; fwrite(&want, sizeof(want), 1, w); }
+                e->build(M);
+                if (w) {
+                    want.nrec = e->img.nrec;
+                    fseek(w, 0, SEEK_SET);
+                    fwrite(&want, sizeof(want), 1, w);
+                    fclose(w);
+                    e->img.f = nullptr; e->img.mode = 0;
+                    rename(tmp.c_str(), image_path);
+                }
+            }
+        }
+        if (!e) throw std::runtime_error("device image: rebuild failed");
+        CUDA_CHECK(cudaDeviceSynchronize());
+        *out = e;
+    });
+    if (rc != STTS_OK && e) { if (e->img.f) fclose(e->img.f); stts_destroy(e); }
     return rc;
 }
 

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "stts_batch_fetch", "stts_set_forced_durations", "stts_debug_fetch", "stts_debug_enable", "stts_last_timing",
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
-    "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks", "stts_infer_stream",
+    "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks", "stts_infer_stream", "stts_create_cached",
 ]
 
 _lib = None
@@ -110,12 +110,20 @@ STAGES = {"xx": 0, "m": 1, "logw": 2, "w_ceil": 3, "z_p": 4, "z": 5, "o": 6}
 class SynthesizerTrn:
     """Drop-in mirror of the reference class (include/SynthesizerTrn.h:9-19) at the ID level."""
 
-    def __init__(self, model_data: np.ndarray, model_size: int | None = None, device: int = 0):
+    def __init__(self, model_data: np.ndarray, model_size: int | None = None, device: int = 0, image_path: str | None = None):
+        """image_path: optional pre-packed device image (stts_create_cached); `self.from_image` tells whether it was used."""
         L = load_library()
         blob = np.ascontiguousarray(model_data, dtype=np.float32)
         nbytes = blob.nbytes if model_size is None else int(model_size)
         h = C.c_void_p()
-        _check(L.stts_create(blob.ctypes.data, nbytes, int(device), C.byref(h)))
+        self.from_image = False
+        if image_path:
+            used = C.c_int32(0)
+            L.stts_create_cached.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+            _check(L.stts_create_cached(blob.ctypes.data, nbytes, int(device), image_path.encode(), C.byref(h), C.byref(used)))
+            self.from_image = bool(used.value)
+        else:
+            _check(L.stts_create(blob.ctypes.data, nbytes, int(device), C.byref(h)))
         self._h = h
         self._L = L
         self.lang_type = L.stts_header_field(h, 1)
