@@ -19,6 +19,7 @@
 
 #include "../../include/stts_b200.h"
 #include "kernels.cuh"
+#include "nb_fused.cuh"
 #include "model.hpp"
 #ifdef STTS_WITH_TC
 #include "conv_tc.cuh"
@@ -166,6 +167,7 @@ struct stts_engine {
     std::vector<int> upRates;
     struct RB {
         std::vector<DConv> c1, c2;
+        std::vector<std::vector<float>> hw1, hb1, hw2, hb2;   // host copies of narrow (<= 8 channel) pairs: kernel-parameter weights of nb_fused.cuh
     };
     std::vector<RB> rbs;
     int nRbK = 0;
@@ -571,6 +573,7 @@ struct stts_engine {
         int n = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
         if (n > 0) sms = n;
+        CUDA_CHECK(nb_device_setup());
         d_flags = dalloc<unsigned int>(4);
         CUDA_CHECK(cudaMemset(d_flags, 0, 16));
         CUDA_CHECK(cudaMallocHost((void**)&h_flags, 16));
@@ -755,6 +758,17 @@ void stts_engine::build(const Model& M) {
         RB rb;
         for (auto& c : G.rbs[i].convs1) rb.c1.push_back(make_conv(c, {}, {}, 1.f, -1, true, true));
         for (auto& c : G.rbs[i].convs2) rb.c2.push_back(make_conv(c, {}, {}, 1.f, -1, true, true));
+        if (!rb.c1.empty() && rb.c1[0].Cin <= 8 && rb.c1.size() == rb.c2.size())
+            for (size_t q = 0; q < rb.c1.size(); ++q) {          // (read back from the device: also valid when the convs came from the image)
+                auto fetch = [&](const float* dptr, size_t n) {
+                    std::vector<float> h(n);
+                    if (dptr && n) CUDA_CHECK(cudaMemcpy(h.data(), dptr, n * 4, cudaMemcpyDeviceToHost));
+                    return h;
+                };
+                const DConv &a = rb.c1[q], &b = rb.c2[q];
+                rb.hw1.push_back(fetch(a.w, (size_t)a.k * a.Cin * a.CoutW)); rb.hb1.push_back(fetch(a.b, a.b ? a.Cout : 0));
+                rb.hw2.push_back(fetch(b.w, (size_t)b.k * b.Cin * b.CoutW)); rb.hb2.push_back(fetch(b.b, b.b ? b.Cout : 0));
+            }
         rbs.push_back(rb);
     }
     if (decType == 0) {
@@ -1236,6 +1250,43 @@ void stts_engine::run() {
         const Seg sseg{d_foff, rate, 0};
         curCls = STTS_CLS_DEC_RB; curRowsTotal = (int64_t)Ft * rate;
         const int ml = maxF * rate;
+        {   // narrow stages (4 / 8 channels): fused ResBlock1 pairs on the CUDA cores (nb_fused.cuh), fp32, any tensor mode
+            static const int env_nb = getenv("STTS_NB_FUSED") ? atoi(getenv("STTS_NB_FUSED")) : 1;
+            bool nbOk = env_nb && (C == 4 || C == 8) && nRbK >= 1;
+            for (int j = 0; j < nRbK && nbOk; ++j) {
+                const RB& rb = rbs[s * nRbK + j];
+                nbOk = rb.c1.size() == rb.c2.size() && !rb.c1.empty() && rb.hw1.size() == rb.c1.size();
+                for (size_t q = 0; q < rb.c1.size() && nbOk; ++q)
+                    nbOk = rb.c1[q].Cin == C && rb.c1[q].Cout == C && rb.c2[q].Cin == C && rb.c2[q].Cout == C && rb.c1[q].CoutW == rb.c2[q].CoutW &&
+                           nb_supported(C, rb.c1[q].k, rb.c1[q].dil, rb.c1[q].padl, rb.c2[q].k, rb.c2[q].dil, rb.c2[q].padl);
+            }
+            if (nbOk) {
+                float* pp[2] = {ws.get<float>(rows * C), ws.get<float>(rows * C)};
+                for (int j = 0; j < nRbK; ++j) {
+                    const RB& rb = rbs[s * nRbK + j];
+                    const int nb = (int)rb.c1.size();
+                    const float* in = xx;
+                    for (int q = 0; q < nb; ++q) {
+                        const bool last = q == nb - 1;
+                        NbP np;
+                        np.x = in; np.y = last ? accb : pp[q & 1]; np.acc = accb; np.seg = sseg; np.d1 = rb.c1[q].dil; np.tr = 0;
+                        np.out_mode = !last || j == 0 ? NB_STORE : (j < nRbK - 1 ? NB_ACCUM : NB_ACCUM_DIV);
+                        if (last && nRbK == 1) np.out_mode = NB_STORE;
+                        np.div = (float)nRbK;
+                        ProfRec pr;
+                        if (profOn) prof_begin(pr, 2.0 * (rb.c1[q].macs_row + rb.c2[q].macs_row) * (double)curRowsTotal);
+                        if (nb_pair_launch(C, rb.c1[q].k, np, rb.hw1[q].data(), rb.hb1[q].empty() ? nullptr : rb.hb1[q].data(), rb.hw2[q].data(),
+                                           rb.hb2[q].empty() ? nullptr : rb.hb2[q].data(), rb.c1[q].CoutW, B, ml, stream) < 0)
+                            throw std::runtime_error("narrow fused pair: unsupported shape (planning bug)");
+                        launch_check();
+                        if (profOn) prof_end(pr);
+                        in = np.y;
+                    }
+                }
+                cur = accb; curC = C;
+                continue;
+            }
+        }
 #ifdef STTS_WITH_TC
         Planes xxP, t1P, xaP;
         bool rbTc = tensor_mode >= 1;
@@ -1245,7 +1296,7 @@ void stts_engine::run() {
         }
         // fused ResBlock1 pairs (rb_fused.cuh): 32/64-channel stages whose every pair fits the fused kernel
         static const int env_fused = getenv("STTS_RB_FUSED") ? atoi(getenv("STTS_RB_FUSED")) : 1;
-        bool rbFused = rbTc && env_fused && (C == 32 || C == 64) && nRbK >= 1 && nRbK <= 3;
+        bool rbFused = rbTc && env_fused && (C == 16 || C == 32 || C == 64) && nRbK >= 1 && nRbK <= 3;
         for (int j = 0; j < nRbK && rbFused; ++j) {
             const RB& rb = rbs[s * nRbK + j];
             if (rb.c1.size() != rb.c2.size() || rb.c1.empty()) rbFused = false;

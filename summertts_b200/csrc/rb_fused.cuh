@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) rb_tiles_kernel(Seg seg, int nseg, int ov
 //   mode 0: ROLE 0 issues A_hi x [W_hi | W_lo] (N = 2C) into main[mt], ROLE 1 issues A_lo x W_hi (N = C) into corr[mt];
 //   mode 1: ROLE r issues A_hi x W_hi (N = C) for M-tile r.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int rb_nmain(int C) { return C == 32 ? 2 : 1; }
+__host__ __device__ constexpr int rb_nmain(int C) { return C <= 32 ? 2 : 1; }
 template <int C, int KIND>
 __device__ __forceinline__ void rb_issuer(const RbP& p, const int mt, const uint32_t abuf_s, const uint32_t t1_s, const uint32_t w_s, const uint32_t tmem,
                                           uint64_t* a_full, uint64_t* m_full, uint64_t* m_empty, uint64_t* c_full, uint64_t* c_empty,
@@ -291,8 +291,10 @@ template <int C>
 __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, const __grid_constant__ CUtensorMap imap) {
     constexpr int G = C / 8;          // 16-byte channel groups per plane
     constexpr int KS = C / 16;        // K = 16 MMA steps per tap
-    constexpr int CH = C / 2;         // columns per epilogue thread (a row is shared by two threads of different warps)
-    constexpr int GH = G / 2;         // channel groups per epilogue thread
+    constexpr int HS = C >= 32 ? 2 : 1;   // column halves: a row is shared by HS threads of different warps (C = 16: one thread per row,
+                                          // epilogue warps 8-15 idle)
+    constexpr int CH = C / HS;        // columns per epilogue thread
+    constexpr int GH = G / HS;        // channel groups per epilogue thread
     extern __shared__ __align__(128) uint8_t rsm[];
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a warp reduction (REDUX writes a uniform register: the role branches below are warp-uniform)
@@ -319,12 +321,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 4);      // one arrival per epilogue set (M-tile, column half)
-            mbar_init(&m_full[2 * i], 1); mbar_init(&m_empty[2 * i], 8);      // one arrival per warp of the M-tile's two sets
-            mbar_init(&m_full[2 * i + 1], 1); mbar_init(&m_empty[2 * i + 1], 8);
-            mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 8);
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2 * HS);      // one arrival per epilogue set (M-tile, column half)
+            mbar_init(&m_full[2 * i], 1); mbar_init(&m_empty[2 * i], 4 * HS);      // one arrival per warp of the M-tile's sets
+            mbar_init(&m_full[2 * i + 1], 1); mbar_init(&m_empty[2 * i + 1], 4 * HS);
+            mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 4 * HS);
         }
-        mbar_init(t1_full, 16);                                        // one arrival per epilogue warp
+        mbar_init(t1_full, 8 * HS);                                    // one arrival per active epilogue warp
         for (int s = 0; s < RB_MAX_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], p.mode ? 2 : 4); }   // issuers that read a stage
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -344,7 +346,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
     long long* rtr = nullptr;
     const int UPT = p.mode ? 64 : max(1, p.usteps / KS);     // taps per promotion unit
 
-    if (warp < 16) {
+    if (warp < 16 && (warp >> 3) >= HS) {
+        // (C = 16: the second column-half warps have nothing to do)
+    } else if (warp < 16) {
         // ================= promotion + epilogues: set (M-tile mt, column half hf), one row x CH columns per thread ==========
         const int wq = warp & 3, mt = (warp >> 2) & 1, hf = warp >> 3;
         const int tl = wq * 32 + lane;                 // TMEM lane = row inside the M-tile
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                     // ---- epilogue 1: t1 = leaky(conv1 + b1), zero outside the utterance, as split-fp16 planes in smem ----
                     if (tile > 0) {                    // the previous tile's output tile aliases T1: its bulk stores must have read it
                         if (tid < 2 * G) bulk_wait_read0();
-                        asm volatile("bar.sync 1, 512;" ::: "memory");
+                        asm volatile("bar.sync 1, %0;" ::"n"(256 * HS) : "memory");
                     }
                     const int tr = it.t0 - p.pad2 + i;
                     const bool valid = tr >= 0 && tr < it.len;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                     // The output tile [2G][OV][16 B] aliases T1, which conv2's MMAs of BOTH M-tiles read (M-tile 0's rows reach
                     // into the second half and the two layouts interleave): every epilogue thread has passed its own
                     // m_full / c_full wait here, so after this barrier all of conv2 has retired.
-                    asm volatile("bar.sync 2, 512;" ::: "memory");
+                    asm volatile("bar.sync 2, %0;" ::"n"(256 * HS) : "memory");
                     RB_TS(2 + mt, tile * 8 + 5);
                     uint8_t* dst = t1 + (size_t)i * 16;
 #pragma unroll
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                     // retired long ago)
                     fence_proxy_async();
                     RB_TS(2 + mt, tile * 8 + 6);
-                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(256 * HS) : "memory");
                     if (tid < 2 * G) {        // one bulk store per (plane, 16-byte channel group): exactly the rows of this utterance
                         const int nrows = min(OV, it.len - it.t0);
                         __half* gdst = p.outp.base + ((size_t)tid * p.outp.rows_p + (size_t)(it.prow_u + it.t0)) * 8;
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(256) mrf_combine_kernel(Planes a, Planes b, Pl
 inline void rb_prepare_weights(RbWeights& r, const float* w /*[k][C][CoutW]*/, int k, int C, int CoutW, int dil, int pad, const float* bias_dev,
                                std::vector<void*>& owned) {
     r.ok = false;
-    if (C != 32 && C != 64) return;
+    if (C != 16 && C != 32 && C != 64) return;
     TcWeights t;
     std::vector<__half> buf;
     if (!tc_pack_weights_host(t, w, k, C, C, CoutW, buf, 8, /*force_merge=*/true)) return;
@@ -705,6 +709,8 @@ inline bool rb_make_map(CUtensorMap* m, const Planes& pl, int box_rows) {
 inline cudaError_t rb_device_setup() {
     cudaError_t e = cudaFuncSetAttribute(rb_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rb_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(rb_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 // x planes (act applied by the producer) -> x' planes.  Returns 1 (launches), < 0 on error.
@@ -753,6 +759,7 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
     if (do_trace) cudaMemsetAsync(trace_buf, 0, 6 * 1024 * 8, stream);
     p.trace = do_trace ? trace_buf : nullptr;
     if (C == 32) rb_pair_kernel<32><<<ctas, RB_THREADS, pl.smem, stream>>>(p, imap);
+    else if (C == 16) rb_pair_kernel<16><<<ctas, RB_THREADS, pl.smem, stream>>>(p, imap);
     else rb_pair_kernel<64><<<ctas, RB_THREADS, pl.smem, stream>>>(p, imap);
     if (do_trace) {   // dump the traced CTA's timeline (debug tool; synchronises)
         --trace_left[C == 64];

@@ -33,7 +33,7 @@ def _oracle(x, cv1, cv2, d, seg, out_leaky):
     return np.concatenate(outs, axis=0)
 
 
-CASES = [(32, 3, 1), (32, 7, 3), (32, 11, 5), (64, 3, 1), (64, 7, 3), (64, 11, 5), (64, 5, 1), (32, 3, 3)]
+CASES = [(32, 3, 1), (32, 7, 3), (32, 11, 5), (64, 3, 1), (64, 7, 3), (64, 11, 5), (64, 5, 1), (32, 3, 3), (16, 3, 1), (16, 7, 3), (16, 11, 5)]
 
 
 @pytest.mark.parametrize("mode", [0, 1])
