@@ -5,6 +5,7 @@
 // src/nn_op call underneath it.  One engine = one GPU, one stream; a batch of utterances is packed
 // along the row dimension (see kernels.cuh).  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
 
 #include <algorithm>
 #include <cmath>
@@ -48,6 +49,11 @@ struct Unsupported : std::runtime_error {
     } while (0)
 
 static thread_local std::string g_last_error;
+
+struct NvtxRange {           // one range per pipeline stage of run(): text encoder / duration predictor / regulator / flow / decoder
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // device-side weight records
@@ -896,6 +902,8 @@ void stts_engine::run() {
     const Seg tseg{d_toff, 1, 0};
     const Seg bseg{d_bseg, 1, 0};
     CUDA_CHECK(cudaEventRecord(ev[0], stream));
+    nvtxRangePushA(injectZ ? "stts:chunk" : "stts:text_encoder");
+    struct PopAll { int n = 1; ~PopAll() { while (n-- > 0) nvtxRangePop(); } } nvtx_guard;   // exception-safe: exactly one range open at any time
     if (tensor_mode >= 1) CUDA_CHECK(cudaMemsetAsync(d_flags, 0, 4, stream));
 
     // ---- token-level workspace ---------------------------------------------------------------
@@ -986,6 +994,7 @@ void stts_engine::run() {
     }
     conv(encProj, x, H, mbuf, inter, tseg, B, maxT);
     CUDA_CHECK(cudaEventRecord(ev[1], stream));
+    nvtxRangePop(); nvtxRangePushA("stts:duration_predictor");
 
     // ---- duration predictor ------------------------------------------------------------------
     curCls = STTS_CLS_DP;
@@ -1056,6 +1065,7 @@ void stts_engine::run() {
     if (Ft <= 0 || (int64_t)Ft > (int64_t)16 << 20) throw ArgError("implausible frame count (length_scale / forced durations too large?)");
     CUDA_CHECK(cudaMemcpyAsync(d_foff, h_foff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaEventRecord(ev[2], stream));
+    nvtxRangePop(); nvtxRangePushA("stts:length_regulator");
 
     // ---- frame-level workspace -----------------------------------------------------------------
     int R = 1;
@@ -1140,6 +1150,7 @@ void stts_engine::run() {
         if (debug) CUDA_CHECK(cudaMemcpyAsync(zp_dbg, z, (size_t)Ft * inter * 4, cudaMemcpyDeviceToDevice, stream));
     }
     CUDA_CHECK(cudaEventRecord(ev[3], stream));
+    nvtxRangePop(); nvtxRangePushA("stts:flow");
     if (stopAfterRegulate) {      // keep z_p for the chunked flow + decoder passes
         const size_t nb = (size_t)Ft * inter * 4;
         if (nb > streamZCap) {
@@ -1225,6 +1236,7 @@ void stts_engine::run() {
         launch_check();
     }
     CUDA_CHECK(cudaEventRecord(ev[4], stream));
+    nvtxRangePop(); nvtxRangePushA("stts:decoder");
 
     // ---- decoder --------------------------------------------------------------------------------
     float* cur = ws.get<float>((size_t)Ft * convPre.Cout);
