@@ -343,6 +343,7 @@ struct TcP {
     const float* acc_src;   // EPI_ACCUM / EPI_ACCUM_DIV: accumulate onto this tensor instead of y (null: y itself)
     long long* trace;   // optional clock64 trace of one CTA (tools/tc_trace.py): [5 roles][1024]
     int dbg;            // timing experiments (STTS_TC_DBG): 1 = skip activation TMA after warm-up, 2 = skip epilogue stores
+    Planes inp; int bulk_in;   // input planes + 1: activation tiles by 1-D bulk copies (default), 0: by tensor-map boxes (STTS_TILE_TMA=1)
     int single;         // throughput mode (stts_set_tensor_path(2)): ONE fp16 MMA per K-step (hi x hi only); the correction MMAs are
                         // not issued and the correction accumulator is not added (the barrier protocol is unchanged)
 };
@@ -354,6 +355,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
+}
+
+// Activation tile [ng groups][nrows][16 B] from planes into shared memory: one 1-D bulk copy per (plane, group) column — each is
+// contiguous in the planes layout.  Measured (tools/tma_bench.cu, profiles/r2_tma_bench.txt): 30.6 B/clk/SM, against 14.4 B/clk/SM
+// for the same tile as ONE tensor-map box {8 halves, rows, groups}: a box with a 16-byte inner extent costs the TMA unit one
+// request per row.  Rows past the utterance are the zero gap rows of the planes (TC_GAP >= every halo); rows_p carries slack
+// (Engine::planes_rows) so a tile that starts at the last row of the last utterance stays inside the allocation.
+__device__ __forceinline__ void planes_tile_g2s(uint8_t* dst, const Planes& pl, int g0, int ng, long long r0, int nrows, uint64_t* bar) {
+    const __half* src = pl.base + ((size_t)g0 * pl.rows_p + r0) * 8;
+    for (int g = 0; g < ng; ++g) bulk_g2s(dst + (size_t)g * nrows * 16, src + (size_t)g * pl.rows_p * 8, (uint32_t)nrows * 16, bar);
 }
 
 // store 8 consecutive channels (one 16-byte chunk) of one row into hi/lo planes
@@ -905,8 +916,13 @@ __global__ void __launch_bounds__(TC_THREADS, (NCT <= 2 ? 2 : 1)) conv_tc_kernel
                     if ((t.dbg & 1) && g >= AR) { mbar_arrive(&a_full[buf]); if (++buf == AR) { buf = 0; ph ^= 1; } continue; }
                     TC_TS(3, g);
                     mbar_expect_tx(&a_full[buf], 2 * box_bytes);
-                    tma_load_3d(dst, &amap, 0, (int)r0, kc * (KC / 8), &a_full[buf]);
-                    tma_load_3d(dst + a_plane, &amap, 0, (int)r0, t.in_groups + kc * (KC / 8), &a_full[buf]);
+                    if (t.bulk_in) {
+                        planes_tile_g2s(dst, t.inp, kc * (KC / 8), KC / 8, r0, XR, &a_full[buf]);
+                        planes_tile_g2s(dst + a_plane, t.inp, t.in_groups + kc * (KC / 8), KC / 8, r0, XR, &a_full[buf]);
+                    } else {
+                        tma_load_3d(dst, &amap, 0, (int)r0, kc * (KC / 8), &a_full[buf]);
+                        tma_load_3d(dst + a_plane, &amap, 0, (int)r0, t.in_groups + kc * (KC / 8), &a_full[buf]);
+                    }
                     if (++buf == AR) { buf = 0; ph ^= 1; }
                 }
             }
@@ -1088,6 +1104,8 @@ inline int tc_conv_launch(const TcWeights& w, const ConvP& p, const Planes& in, 
     t.colsplit = w.colsplit;
     alignas(64) CUtensorMap amap;
     if (!tc_make_map(&amap, in, t.xr, w.KC)) return -1;
+    static const int env_tile_tma = getenv("STTS_TILE_TMA") ? atoi(getenv("STTS_TILE_TMA")) : 0;
+    t.inp = in; t.bulk_in = env_tile_tma ? 0 : 1;
     dim3 g(ctas, 1, 1);
     static const int env_verbose = getenv("STTS_TC_VERBOSE") ? atoi(getenv("STTS_TC_VERBOSE")) : 0;
     if (env_verbose > 0) {

@@ -250,7 +250,7 @@ struct stts_engine {
 #ifdef STTS_WITH_TC
     void* planeScratch = nullptr;
     size_t planeScratchCap = 0;
-    static size_t planes_rows(int64_t rows_total, int nseg) { return (size_t)rows_total + (size_t)2 * nseg * TC_GAP + 256; }
+    static size_t planes_rows(int64_t rows_total, int nseg) { return (size_t)rows_total + (size_t)2 * nseg * TC_GAP + 512; }   // slack: a 2 x 128-row tile (+ halos) starting at the last valid row stays in the allocation (bulk tile loads do not clip)
     static size_t planes_bytes(int64_t rows_total, int nseg, int C) { return planes_rows(rows_total, nseg) * (size_t)C * 4; }
     Planes scratch_planes(int64_t rows_total, int nseg, int C) {
         const size_t need = planes_bytes(rows_total, nseg, C);
@@ -580,6 +580,8 @@ struct stts_engine {
         CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
         if (n > 0) sms = n;
         CUDA_CHECK(nb_device_setup());
+        CUDA_CHECK(cudaFuncSetAttribute(ms_tail_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(ms_tail_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         d_flags = dalloc<unsigned int>(4);
         CUDA_CHECK(cudaMemset(d_flags, 0, 16));
         CUDA_CHECK(cudaMallocHost((void**)&h_flags, 16));
@@ -816,7 +818,9 @@ void stts_engine::build(const Model& M) {
         }
     }
     if (isMS == 1) emg = upload(M.emg, (size_t)spkNum * gin);
-    CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(relattn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     device_setup();
     // constant DFT tables
     float c16[16], s16[16];
@@ -969,12 +973,12 @@ void stts_engine::run() {
         EncL& L = enc[i];
         conv(L.qkv, x, H, qkv, 3 * H, tseg, B, maxT);
         {
-            dim3 g((maxT + 15) / 16, nHeads, B);
-            size_t sm = ((size_t)16 * kc + 2 * 32 * (kc + 4) + 2 * relRows * kc + 16 * 16) * sizeof(float);
-            if (kc == 96) relattn_kernel<96><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
-            else if (kc == 64) relattn_kernel<64><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
-            else if (kc == 32) relattn_kernel<32><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
-            else relattn_kernel<128><<<g, 128, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
+            dim3 g((maxT + RA_QT - 1) / RA_QT, nHeads, B);
+            size_t sm = ((size_t)RA_QT * kc + 2 * 32 * (kc + 4) + 2 * relRows * kc + RA_QT * 16) * sizeof(float);
+            if (kc == 96) relattn_kernel<96><<<g, RA_THREADS, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
+            else if (kc == 64) relattn_kernel<64><<<g, RA_THREADS, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
+            else if (kc == 32) relattn_kernel<32><<<g, RA_THREADS, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
+            else relattn_kernel<128><<<g, RA_THREADS, sm, stream>>>(qkv, att, L.ek, L.ev, tseg, H, win, relRows);
             launch_check();
         }
         conv(L.o, att, H, y, H, tseg, B, maxT);
@@ -1075,7 +1079,7 @@ void stts_engine::run() {
     size_t need = tokEnd + 4096 + (size_t)(1 << 20);   // (+ super-tile tables of the fused ResBlock1 pairs)
     const int WH = wnHidden;
     need += ((size_t)Ft * (inter * 2 + WH * 3)) * 4 + 8 * 256;
-    need += 3 * ((size_t)Ft + 2 * (size_t)B * 64 + 256) * WH * 4 + 4096;   // split-fp16 planes of h / acts / skip
+    need += 3 * (planes_bytes(Ft, B, WH) + 256) + 4096;   // split-fp16 planes of h / acts / skip
     {
         size_t rows = Ft;
         need += rows * convPre.Cout * 4 + 256;
@@ -1083,7 +1087,7 @@ void stts_engine::run() {
         for (size_t i = 0; i < ups.size(); ++i) {
             rr *= upRates[i];
             need += ((size_t)Ft * rr * stageC[i] * 4 + 256) * 5;                                  // xx / t1 / xa / accb / accT
-            need += 6 * (((size_t)Ft * rr + 2 * (size_t)B * 64 + 256) * stageC[i] * 4 + 256);   // planes xx / t1 / xa, or xx / 2 ping-pong / 3 branch outputs (fused pairs)
+            need += 6 * (planes_bytes((int64_t)Ft * rr, B, stageC[i]) + 256);   // planes xx / t1 / xa, or xx / 2 ping-pong / 3 branch outputs (fused pairs)
         }
         if (decType != 0) {
             const size_t fr = (size_t)Ft * R + B;
@@ -1415,6 +1419,7 @@ void stts_engine::run() {
         cur = accb; curC = C;
     }
     float* o = ws.get<float>((size_t)std::max<int64_t>(St, 1));
+    bool tailDone = false;
     curCls = STTS_CLS_DEC_TAIL; curRowsTotal = (int64_t)Ft * rate + (decType == 0 ? 0 : B);
     if (decType == 0) {
         // leaky(0.01) -> conv_post -> tanh: Generator_hifigan.cpp:176-180
@@ -1433,6 +1438,20 @@ void stts_engine::run() {
             launch_check();
         }
         conv(subPost, xr, curC, sp, subPost.Cout, sfr, B, maxF * rate + 1);
+        static const int env_tail = getenv("STTS_TAIL_FUSED") ? atoi(getenv("STTS_TAIL_FUSED")) : 1;
+        if (decType != 2 && subBands == 4 && env_tail) {
+            // exp / pi*sin, inverse DFT, overlap-add, synthesis FIR and the PCM cast in ONE launch, intermediates in shared memory
+            d_pcm = ws.get<int16_t>((size_t)std::max<int64_t>(St, 1));
+            static const int env_ti = getenv("STTS_TAIL_TI") ? atoi(getenv("STTS_TAIL_TI")) : 256;
+            const int ti = env_ti == 512 ? 512 : (env_ti == 128 ? 128 : 256);
+            dim3 g((maxF * rate * 4 + ti - 1) / ti, B);
+            const Seg sso{d_foff, rate * 16, 0};
+            if (ti == 512) ms_tail_kernel<512><<<g, 256, ms_tail_smem(512), stream>>>(sp, subPost.Cout, msW, msB, o, d_pcm, sfr, sy, sso);
+            else if (ti == 128) ms_tail_kernel<128><<<g, 256, ms_tail_smem(128), stream>>>(sp, subPost.Cout, msW, msB, o, d_pcm, sfr, sy, sso);
+            else ms_tail_kernel<256><<<g, 256, ms_tail_smem(256), stream>>>(sp, subPost.Cout, msW, msB, o, d_pcm, sfr, sy, sso);
+            launch_check();
+            tailDone = true;
+        } else {
         istft_frames_kernel<<<(frRows + 6) / 7, 256, 0, stream>>>(sp, subPost.Cout, frames, (int)frRows, subBands);
         launch_check();
         {
@@ -1448,10 +1467,13 @@ void stts_engine::run() {
             synth_fir_kernel<<<g, 256, 0, stream>>>(yb, msW, msB, o, sy, Seg{d_foff, rate * 16, 0});
             launch_check();
         }
+        }
     }
-    d_pcm = ws.get<int16_t>((size_t)std::max<int64_t>(St, 1));
-    pcm_kernel<<<(St + 255) / 256, 256, 0, stream>>>(o, d_pcm, (size_t)St);
-    launch_check();
+    if (!tailDone) {
+        d_pcm = ws.get<int16_t>((size_t)std::max<int64_t>(St, 1));
+        pcm_kernel<<<(St + 255) / 256, 256, 0, stream>>>(o, d_pcm, (size_t)St);
+        launch_check();
+    }
     CUDA_CHECK(cudaEventRecord(ev[5], stream));
     if (tensor_mode >= 1) CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, 4, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -325,11 +325,12 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
 // qkv: [rows][3*C] (q | k | v), one CTA = 16 queries of one head of one utterance, 4 warps.
 // KC (channels per head) must be a multiple of 32 and <= 128.
 // ----------------------------------------------------------------------------------------------
+constexpr int RA_QPW = 8, RA_WARPS = 8, RA_THREADS = RA_WARPS * 32, RA_QT = RA_QPW * RA_WARPS;   // 64 queries per CTA
 template <int KC>
-__global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+__global__ void __launch_bounds__(RA_THREADS) relattn_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                        const float* __restrict__ embK, const float* __restrict__ embV,
                                                        Seg seg, int C, int win, int relRows) {
-    constexpr int NL = KC / 32, KP = KC + 4, QT = 16;   // KP % 4 == 0: float4 rows; 16*lane byte skew: conflict-free quarter-warps
+    constexpr int NL = KC / 32, KP = KC + 4, QT = RA_QT, QW = RA_QPW;   // KP % 4 == 0: float4 rows; 16*lane byte skew: conflict-free quarter-warps
     extern __shared__ __align__(16) float sm[];
     float* qs = sm;                    // [QT][KC]
     float* ks = qs + QT * KC;          // [32][KP]
@@ -345,35 +346,36 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
     const int ld = 3 * C;
     const float inv = sqrtf((float)KC);
     const int R = 2 * win + 1;
-    for (int i = tid; i < QT * KC; i += 128) {
+    for (int i = tid; i < QT * KC; i += RA_THREADS) {
         const int r = i / KC, c = i % KC;
         const int t = q0 + r;
         qs[i] = t < len ? qkv[(size_t)(seg0 + t) * ld + h * KC + c] / inv : 0.f;
     }
-    for (int i = tid; i < R * KC; i += 128) {
+    for (int i = tid; i < R * KC; i += RA_THREADS) {
         const int r = i / KC, c = i % KC;   // file is col-major (rows x cols): e(r,c) = p[c*rows + r]
         ek[i] = __ldg(embK + (size_t)c * relRows + r);
         ev[i] = __ldg(embV + (size_t)c * relRows + r);
     }
     __syncthreads();
-    for (int i = tid; i < QT * R; i += 128) {
+    for (int i = tid; i < QT * R; i += RA_THREADS) {
         const int r = i / R, d = i % R;
         float s = 0.f;
         for (int c = 0; c < KC; ++c) s = fmaf(qs[r * KC + c], ek[d * KC + c], s);
         rk[r * 16 + d] = s;
     }
-    // per-warp state for its 4 queries (processed jointly: every K/V value read from smem feeds 4 FMAs)
-    float m[4], l[4], acc[4][NL], sband[4];
+    // per-warp state for its QW queries (processed jointly: every K/V value read from smem feeds QW FMAs; a CTA of 64 queries
+    // stages each K/V block once for 8 warps -- round 1 used 16 queries per CTA and re-staged K/V four times as often)
+    float m[QW], l[QW], acc[QW][NL], sband[QW];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < QW; ++a) {
         m[a] = -INFINITY; l[a] = 0.f; sband[a] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < NL; ++c) acc[a][c] = 0.f;
     }
-    const int qb = warp * 4;
+    const int qb = warp * QW;
     for (int j0 = 0; j0 < len; j0 += 32) {
         __syncthreads();
-        for (int i = tid; i < 32 * (KC / 4); i += 128) {
+        for (int i = tid; i < 32 * (KC / 4); i += RA_THREADS) {
             const int r = i / (KC / 4), c4 = (i % (KC / 4)) * 4;
             const int t = j0 + r;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
@@ -387,20 +389,22 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
         }
         __syncthreads();
         const int j = j0 + lane;
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        float s[QW];
+#pragma unroll
+        for (int a = 0; a < QW; ++a) s[a] = 0.f;
 #pragma unroll 4
         for (int c = 0; c < KC; c += 4) {
             const float4 kv = *reinterpret_cast<const float4*>(ks + lane * KP + c);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < QW; ++a) {
                 const float4 qv = *reinterpret_cast<const float4*>(qs + (qb + a) * KC + c);   // broadcast
                 s[a] = fmaf(qv.x, kv.x, s[a]); s[a] = fmaf(qv.y, kv.y, s[a]);
                 s[a] = fmaf(qv.z, kv.z, s[a]); s[a] = fmaf(qv.w, kv.w, s[a]);
             }
         }
-        float pj[4];
+        float pj[QW];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < QW; ++a) {
             const int i = q0 + qb + a;
             const int d = j - i + win;
             if (d >= 0 && d < R) s[a] += rk[(qb + a) * 16 + d];
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
 #pragma unroll
             for (int c = 0; c < NL; ++c) v[c] = vs[jj * KP + lane + 32 * c];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < QW; ++a) {
                 const float pb = __shfl_sync(0xffffffffu, pj[a], jj);
 #pragma unroll
                 for (int c = 0; c < NL; ++c) acc[a][c] = fmaf(pb, v[c], acc[a][c]);
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(128) relattn_kernel(const float* __restrict__ 
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < QW; ++a) {
         const int qi = qb + a;
         const int i = q0 + qi;
         if (i >= len) continue;   // warp-uniform
@@ -844,6 +848,111 @@ __global__ void pcm_kernel(const float* __restrict__ o, int16_t* __restrict__ pc
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pcm[i] = (int16_t)__float2int_rz(o[i] * 32737.0f);
 }
+
+// K15. The whole 4-band tail in one launch: K11 + K12 + K13 + K14 over a tile of TI band samples with the halos each stage needs,
+// all intermediates in shared memory (round 1 wrote and re-read frames [rows][64], yb [4 rows][4] and o through HBM in four
+// launches).  Same arithmetic, same order: bit-identical to the four kernels.  Generator_MS.cpp:210-229 / Generator_MBB.cpp:176-203,
+// iStft.cpp:63-123, SynthesizerTrn.cpp:389-396.
+template <int MT_TI>                             // band samples per CTA (-> 4 MT_TI output samples)
+__global__ void __launch_bounds__(256) ms_tail_kernel(const float* __restrict__ sp, int ldS, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ o, int16_t* __restrict__ pcm, Seg sfr, Seg sy, Seg so) {
+    constexpr int MT_NF = MT_TI / 4 + 8;          // frame rows a tile touches
+    extern __shared__ __align__(16) float mtsm[];
+    float* re = mtsm;                             // [MT_NF][36]
+    float* im = re + MT_NF * 36;                  // [MT_NF][36]
+    float* fr = im + MT_NF * 36;                  // [MT_NF][64]
+    float* ybs = fr + MT_NF * 64;                 // [MT_TI + 16][4]
+    float* wsm = ybs + (MT_TI + 16) * 4;          // [63][4]
+    __shared__ float s_cos[16], s_sin[16], s_hann[16], s_hp[16];
+    const int u = blockIdx.y;
+    const int ny = seg_len(sy, u);
+    const int i0 = blockIdx.x * MT_TI;
+    if (i0 >= ny) return;
+    const int nfr = seg_len(sfr, u), f0 = seg_start(sfr, u);
+    const int tid = threadIdx.x;
+    if (tid < 16) { s_cos[tid] = c_cos16[tid]; s_sin[tid] = c_sin16[tid]; s_hann[tid] = c_hann[tid]; s_hp[tid] = c_hann_pow[tid]; }
+    for (int i = tid; i < 63 * 4; i += 256) wsm[i] = w[i];
+    const int jbase = (i0 - 12) >> 2;             // first frame row of the tile (arithmetic shift: may be negative)
+    // ---- K11 phase 1: exp / pi*sin -> complex bins ---------------------------------------------------
+    for (int e = tid; e < MT_NF * 36; e += 256) {
+        const int jl = e / 36, q = e - jl * 36;
+        const int j = jbase + jl;
+        float r_ = 0.f, i_ = 0.f;
+        if (j >= 0 && j < nfr) {
+            const int b = q / 9, k = q - b * 9;
+            const float* row = sp + (size_t)(f0 + j) * ldS + b * 18;
+            const float mag = expf(row[k]);
+            const float ph = sinf(row[9 + k]) * 3.14159265358979323846f;
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            r_ = mag * cs; i_ = mag * sn;
+        }
+        re[e] = r_; im[e] = i_;
+    }
+    __syncthreads();
+    // ---- K11 phase 2: 16-point real inverse DFT + window --------------------------------------------
+    for (int e = tid; e < MT_NF * 64; e += 256) {
+        const int jl = e >> 6, q = e & 63;
+        const int b = q >> 4, n = q & 15;
+        const float* rr = re + jl * 36 + b * 9;
+        const float* ii = im + jl * 36 + b * 9;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const int mI = (k * n) & 15;
+            acc += rr[k] * s_cos[mI] - ii[k] * s_sin[mI];
+        }
+        const float x = (rr[0] + ((n & 1) ? -rr[8] : rr[8]) + 2.0f * acc) * (1.0f / 16.0f);
+        fr[e] = x * s_hann[n];
+    }
+    __syncthreads();
+    // ---- K12: overlap-add + window-sum normalisation + centre crop ------------------------------------
+    for (int e = tid; e < (MT_TI + 16) * 4; e += 256) {
+        const int il = e >> 2, b = e & 3;
+        const int i = i0 - 8 + il;
+        float acc = 0.f;
+        if (i >= 0 && i < ny) {
+            const int pos = i + 8;
+            float wsum = 0.f;
+            int jlo = (pos - 15 + 3) >> 2;
+            if (jlo < 0) jlo = 0;
+            int jhi = pos >> 2;
+            if (jhi > nfr - 1) jhi = nfr - 1;
+            for (int j = jlo; j <= jhi; ++j) {
+                const int n = pos - 4 * j;
+                acc += fr[(j - jbase) * 64 + b * 16 + n];
+                wsum += s_hp[n];
+            }
+            if (wsum > 1e-14f) acc = acc / wsum;
+        }
+        ybs[e] = acc;
+    }
+    __syncthreads();
+    // ---- K13 + K14: zero-stuff x4 (gain 4) + 63-tap synthesis FIR, float waveform + int16 PCM ----------
+    const int ns = seg_len(so, u);
+    const size_t s0 = (size_t)seg_start(so, u);
+    for (int sl = tid; sl < 4 * MT_TI; sl += 256) {
+        const int sidx = 4 * i0 + sl;
+        if (sidx >= ns) break;
+        float acc = 0.f;
+        const int k0 = ((31 - sidx) % 4 + 4) % 4;
+        for (int k = k0; k < 63; k += 4) {
+            const int p = sidx + k - 31;
+            if (p < 0) continue;
+            const int i = p >> 2;
+            if (i >= ny) break;
+            const float4 v = *reinterpret_cast<const float4*>(ybs + (size_t)(i - (i0 - 8)) * 4);
+            acc = fmaf(v.x * 4.0f, wsm[k * 4 + 0], acc);
+            acc = fmaf(v.y * 4.0f, wsm[k * 4 + 1], acc);
+            acc = fmaf(v.z * 4.0f, wsm[k * 4 + 2], acc);
+            acc = fmaf(v.w * 4.0f, wsm[k * 4 + 3], acc);
+        }
+        if (bias) acc += bias[0];
+        o[s0 + sidx] = acc;
+        pcm[s0 + sidx] = (int16_t)__float2int_rz(acc * 32737.0f);
+    }
+}
+inline size_t ms_tail_smem(int ti) { const size_t nf = ti / 4 + 8; return (nf * 36 * 2 + nf * 64 + (size_t)(ti + 16) * 4 + 63 * 4) * sizeof(float); }
 
 // column 0 copy (Generator_Istft: single band -> waveform)
 __global__ void copy_kernel(const float* __restrict__ a, float* __restrict__ b, size_t n) {

@@ -1,27 +1,29 @@
-// pc_fused.cuh — wide-channel Conv1d on planes with the epilogue staged through shared memory (sm_100a, tcgen05 + TMEM + TMA):
+// pc_fused.cuh — wide-channel Conv1d on planes, activation tile resident per row tile, weights streamed (sm_100a, tcgen05 + TMEM + bulk copies):
 // the two convs of a WaveNet layer (WN::forward, src/modules/WN.cpp:100-149; nn_conv1d.cpp:118-199)
 //
 //   EPI_GATE   acts = tanh(a[:, :H] + g) * sigmoid(a[:, H:] + g),  a = conv_k5(h)              (in_layer + fused_add_tanh_sigmoid_multiply,
 //                                                                                               WN.cpp:85-98,118-126)
 //   EPI_RS     rs = conv_1x1(acts);  h += rs[:, :H];  skip (+)= rs[:, H:]   (last layer: skip += rs)   (WN.cpp:128-146)
 //
-// Like rb_fused.cuh, every tensor is split-fp16 PLANES in HBM (8 x = hi + lo, [C/8][padded row][8], hi then lo) and no epilogue
-// thread touches global memory:
-//   * a work item = (128-row tile of one utterance, PAIR of 64-column output chunks).  The activation tile [2 Cin/8][XR][16 B]
-//     arrives by one TMA box and feeds both chunks of the pair; each chunk owns a TMEM slot: `main` (128 columns: hi*hi | hi*lo of
-//     one merged N = 128 MMA per K-step) + `corr` (64 columns: lo*hi).  The two slots alternate per promotion unit (8 K-steps = 2
-//     weight stages of 64 input channels), so a drain (tcgen05.ld) overlaps the other slot's MMAs.
+// Like rb_fused.cuh, every tensor is split-fp16 PLANES in HBM (8 x = hi + lo, [C/8][padded row][8], hi then lo):
+//   * a work item = (128-row tile of one utterance, PAIR of 64-column output chunks); items are tile-major and every CTA owns a
+//     CONTIGUOUS range of them, so the activation tile [2 Cin/8][XR][16 B] (one 1-D bulk copy per (plane, group) column) is
+//     loaded once per tile and feeds all the chunk pairs of that tile that fall into the range.
+//   * each chunk of the pair owns a TMEM slot of TWO accumulator buffers (128 columns each: hi*hi | hi*lo + lo*hi).  Promotion
+//     units (8 K-steps = 2 weight stages of 64 input channels) alternate between the buffers and between two issuer threads:
+//     the drain (tcgen05.ld -> fp32 registers) of unit u overlaps the MMAs of unit u + 1 of the same chunk AND the other chunk's.
+//     The correction product A_lo x W_hi has the scale of the hi*lo half and accumulates onto it (same issuer thread, program order).
 //   * weights stream from L2 through a bulk-copy ring in 16 KB stages [64 ch / 8][hi rows 64 | lo rows 64][8 halves].
-//   * EPI_RS reads-modifies-writes the residual streams IN SHARED MEMORY: the producer TMA-loads the chunk's h / skip planes tile
+//   * EPI_RS reads-modifies-writes the residual streams IN SHARED MEMORY: the producer loads the chunk's h / skip planes tile
 //     into the staging buffer, the epilogue adds the conv result in place (x8 domain), bulk async stores write it back.
-//   * EPI_GATE stages 32 acts channels per chunk and bulk-stores them.
+//   * EPI_GATE stores the 32 acts channels of a chunk straight from registers (lane = row: each warp store is 512 contiguous bytes).
 // Arithmetic modes as in rb_fused.cuh (0: merged split-fp16 + promotion, fp32-accurate; 1: one fp16 MMA per K-step).
 #pragma once
 #include "rb_fused.cuh"
 
 namespace stts {
 
-constexpr int PC_THREADS = 672;     // warps 0-15: epilogue sets (slot x column half x lane quarter); 16-19: issuers (kind x slot); 20: producer
+constexpr int PC_THREADS = 672;     // warps 0-15: epilogue sets (slot x column half x lane quarter); 16-19: issuers (slot x accumulator buffer); 20: producer
 constexpr int PC_NCH = 64;          // output columns per chunk
 constexpr int PC_KC = 64;           // input channels per weight stage
 constexpr int PC_STAGE = PC_KC * 2 * PC_NCH * 2;    // 16 KB
@@ -49,7 +51,11 @@ struct PcP {
     unsigned int* flags;
     int ncta;                        // CTAs per cluster (1 or 2): with 2, each CTA fetches HALF of every weight stage and multicasts it to both
                                      // (the two CTAs work on the same chunk pair of two different row tiles), halving the L2 -> SM weight traffic
-    int nclu_items;                  // cluster work items: npairs * ceil(ntiles / ncta)
+    int nclu_items;                  // cluster work items: npairs * ceil(ntiles / ncta), tile-major (w = tile group * npairs + pair)
+    int per;                         // items per cluster: cluster c owns the contiguous range [c * per, (c + 1) * per)
+    Planes inp; int bulk_in;         // input planes; 1: tiles by 1-D bulk copies (planes_tile_g2s), 0: tensor-map boxes (STTS_TILE_TMA=1)
+    int dbg;                         // timing experiments (STTS_PC_DBG; results are garbage): 1 = weight stages are not copied, 2 = MMAs are not issued, 4 = no epilogue math / stores
+    long long* trace;                // STTS_TC_TRACE_BUILD: per-role cycle counters of CTA 0: [role][8]
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -69,90 +75,102 @@ __device__ __forceinline__ uint8_t* pc_cell(uint8_t* stg, int groups, int plane,
     return stg + ((size_t)(plane * groups + g) * 128 + r) * 16;
 }
 
-template <int KIND>
-__device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const uint32_t a_s0, const uint32_t w_s, const uint32_t tmem,
-                                          uint64_t* a_full, uint64_t* a_empty, uint64_t* m_full, uint64_t* m_empty, uint64_t* c_full,
-                                          uint64_t* c_empty, uint64_t* b_full, uint64_t* b_empty) {
+// ring entry `e` (0 .. 2 nst - 1: stage-major, slot-minor) of an item whose first entry sits at (base_slot, base_ph)
+__device__ __forceinline__ void pc_ring_at(int base_slot, uint32_t base_ph, int e, int nb, int& slot_r, uint32_t& ph_r) {
+    const int q = base_slot + e, wrap = q / nb;
+    slot_r = q - wrap * nb;
+    ph_r = base_ph ^ (uint32_t)(wrap & 1);
+}
+
+// MMA issuer (slot, b): every promotion unit u = b (mod 2) of the slot's chunk goes into accumulator buffer b — main product
+// A_hi x [W_hi | W_lo] (N = 128) and correction A_lo x W_hi (N = 64, accumulated onto the hi*lo half) from the SAME thread, so
+// their order in the tensor pipe is the program order.  The two issuers of a slot alternate units: while buffer b drains, the
+// other buffer's MMAs run.  Throughput mode: ONE N = 64 MMA per K-step, issuer b takes the stages st = b (mod 2), no promotion.
+__device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const int b, const int w0, const int w1, const int rank, const uint32_t a_s0,
+                                          const uint32_t w_s, const uint32_t tmem, uint64_t* a_full, uint64_t* a_empty, uint64_t* acc_full,
+                                          uint64_t* acc_empty, uint64_t* b_full, uint64_t* b_empty) {
     const int mode = p.mode;
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(((mode || KIND == 1) ? PC_NCH : 2 * PC_NCH) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_m = (1u << 4) | ((uint32_t)((mode ? PC_NCH : 2 * PC_NCH) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_c = (1u << 4) | ((uint32_t)(PC_NCH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t b_lbo = 2 * PC_NCH * 16;
     constexpr uint32_t b_k16 = (2 * b_lbo) >> 4;
     const uint64_t b_desc0 = ((uint64_t)((b_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46) | (uint64_t)((w_s & 0x3FFFFu) >> 4);
     const uint32_t a_lbo = (uint32_t)p.xr * 16;
     const uint64_t a_bits = ((uint64_t)((a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     const uint32_t a_k16 = (2 * a_lbo) >> 4;
-    const uint32_t a_s = a_s0 + ((mode == 0 && KIND == 1) ? (uint32_t)p.G * a_lbo : 0u);        // mode 0 corr reads the lo plane
-    const uint32_t d_t = tmem + (uint32_t)slot * 192 + (KIND == 1 ? 128u : 0u);
-    uint64_t* full_bar = KIND == 0 ? &m_full[slot] : &c_full[slot];
-    uint64_t* empty_bar = KIND == 0 ? &m_empty[slot] : &c_empty[slot];
-    const int SPU = mode ? (1 << 20) : max(1, p.usteps / 4);      // weight stages per promotion unit (4 K-steps per stage)
+    const uint32_t a_lo = (uint32_t)p.G * a_lbo;                    // the lo plane follows the hi plane in the tile
+    const uint32_t d_m = tmem + (uint32_t)(slot * 256 + b * 128), d_c = d_m + 64u;
+    uint64_t* full_bar = &acc_full[slot * 2 + b];
+    uint64_t* empty_bar = &acc_empty[slot * 2 + b];
+    const int nst = p.nst, nb = p.nb;
+    const int SPU = max(1, p.usteps / 4);                           // weight stages per promotion unit (4 K-steps per stage)
     const int kcs = p.G / 8;                                        // 64-channel blocks per tap
-    uint32_t af_par = 0, e_par = 1;
-    int bs = 0; uint32_t bph = 0;
-    const int W = p.nclu_items, step = gridDim.x / p.ncta;
-    const int rank = p.ncta == 2 ? (int)cluster_rank() : 0;
     const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
-    for (int w = blockIdx.x / p.ncta; w < W; w += step) {
-        const int pair = w % p.npairs, ti = (w / p.npairs) * p.ncta + rank;
-        const bool active = pair * 2 + slot < p.nchunks && ti < p.ntiles;
-        if (ti >= p.ntiles) {                      // a cluster's odd tail: no tile for this CTA, only the weight-stage protocol runs
-            for (int s = 0; s < 2 * p.nst; ++s) {
-                const int slot_r = bs; const uint32_t ph_r = bph;
-                if (++bs == p.nb) { bs = 0; bph ^= 1; }
-                if ((s & 1) != slot) continue;
-                mbar_wait(&b_full[slot_r], ph_r);
-                if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
-            }
-            continue;
-        }
-        mbar_wait(a_full, af_par); af_par ^= 1;
-        tc_fence_after();
-        const int nst = p.nst;
-        const int NU = (mode || KIND == 1) ? 1 : (nst + SPU - 1) / SPU;
-        int s_done = 0;
+    uint32_t af_par = 0, e_par = 1;
+    int rs0 = 0; uint32_t rp0 = 0;                                  // ring position of the item's first entry
+    int prev_tg = -1;
+#ifdef STTS_TC_TRACE_BUILD
+    long long t_a = 0, t_e = 0, t_b = 0, t_all = clock64(), tt;
+#define PC_T0() tt = clock64()
+#define PC_T1(acc) acc += clock64() - tt
+#else
+#define PC_T0()
+#define PC_T1(acc)
+#endif
 #pragma unroll 1
-        for (int un = 0; un < NU; ++un) {
-            const int s1 = NU == 1 ? nst : min(nst, s_done + SPU);
-            if (active) { mbar_wait(empty_bar, e_par); e_par ^= 1; tc_fence_after(); }
-            uint32_t acc = 0u;
+    for (int w = w0; w < w1; ++w) {
+        const int pair = w % p.npairs, tg = w / p.npairs, ti = tg * p.ncta + rank;
+        const bool has_tile = ti < p.ntiles;                        // (a cluster's odd tail: only the weight-stage protocol runs)
+        const bool active = has_tile && pair * 2 + slot < p.nchunks;
+        if (has_tile && tg != prev_tg) { PC_T0(); mbar_wait(a_full, af_par); af_par ^= 1; PC_T1(t_a); tc_fence_after(); }
+        prev_tg = tg;
+        // Both issuers of the slot walk EVERY stage of the slot's chunk and wait for its weights, whoever owns the stage: a ring
+        // entry is refilled only after both have passed it, so neither can fall a whole mbarrier phase behind a ring slot
+        // (a parity wait cannot tell fill n from fill n + 2).
+        uint32_t acc = 0u;
 #pragma unroll 1
-            for (int s = s_done; s < s1; ++s) {
-                // ring entries alternate slot 0 / slot 1 of the same stage index; every issuer walks all of them
-#pragma unroll 1
-                for (int q = 0; q < 2; ++q) {
-                    const int slot_r = bs; const uint32_t ph_r = bph;
-                    if (++bs == p.nb) { bs = 0; bph ^= 1; }
-                    if (q != slot) continue;
-                    if (mode && ((s & 1) != KIND)) {          // not this issuer's stage: just release it
-                        mbar_wait(&b_full[slot_r], ph_r);
-                        if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
-                        continue;
-                    }
-                    mbar_wait(&b_full[slot_r], ph_r);
-                    tc_fence_after();
-                    if (active) {
-                        const int tap = s / kcs, kc = s - tap * kcs;
-                        const uint64_t da = a_bits | (uint64_t)(((a_s + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(kc * 8) * a_lbo) & 0x3FFFFu) >> 4);
-                        const uint64_t db = b_desc0 + (uint32_t)slot_r * (uint32_t)(PC_STAGE >> 4);
+        for (int st = 0; st < nst; ++st) {
+            const bool own = mode ? ((st & 1) == b) : (((st / SPU) & 1) == b);
+            const bool first = mode ? (st == b) : (st % SPU == 0);
+            const bool last = mode ? (st + 2 >= nst) : (st % SPU == SPU - 1 || st == nst - 1);
+            if (own && active && first) { PC_T0(); mbar_wait(empty_bar, e_par); e_par ^= 1; PC_T1(t_e); tc_fence_after(); acc = 0u; }
+            int slot_r; uint32_t ph_r;
+            pc_ring_at(rs0, rp0, 2 * st + slot, nb, slot_r, ph_r);
+            PC_T0(); mbar_wait(&b_full[slot_r], ph_r); PC_T1(t_b);
+            tc_fence_after();
+            if (own && active && !(p.dbg & 2)) {
+                const int tap = st / kcs, kc = st - tap * kcs;
+                const uint64_t da = a_bits | (uint64_t)(((a_s0 + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(kc * 8) * a_lbo) & 0x3FFFFu) >> 4);
+                const uint64_t dl = a_bits | (uint64_t)(((a_s0 + a_lo + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(kc * 8) * a_lbo) & 0x3FFFFu) >> 4);
+                const uint64_t db = b_desc0 + (uint32_t)slot_r * (uint32_t)(PC_STAGE >> 4);
+                if (mode) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_t, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc, ks == 0 ? acc : 1u);
-                        acc = 1u;
+                    for (int ks = 0; ks < 4; ++ks) tc_mma_f16(d_m, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc_m, ks == 0 ? acc : 1u);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        tc_mma_f16(d_m, da + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc_m, ks == 0 ? acc : 1u);
+                        tc_mma_f16(d_c, dl + (uint32_t)(ks * a_k16), db + (uint32_t)(ks * b_k16), idesc_c, 1u);
                     }
-                    if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
                 }
+                acc = 1u;
             }
-            s_done = s1;
-            if (active) tc_commit(full_bar);
+            if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
+            if (own && active && last) tc_commit(full_bar);
         }
-        tc_commit(a_empty);          // this issuer's reads of the activation tile have retired
+        { int s2; uint32_t p2; pc_ring_at(rs0, rp0, 2 * nst, nb, s2, p2); rs0 = s2; rp0 = p2; }
+        if (has_tile && (w + 1 == w1 || (w + 1) / p.npairs != tg)) tc_commit(a_empty);   // this issuer's reads of the activation tile have retired
     }
+#ifdef STTS_TC_TRACE_BUILD
+    if (p.trace && blockIdx.x == 0) { long long* o = p.trace + (b * 2 + slot) * 8; o[0] = clock64() - t_all; o[1] = t_a; o[2] = t_e; o[3] = t_b; }
+#endif
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __grid_constant__ CUtensorMap imap, const __grid_constant__ CUtensorMap rmap0,
                                                            const __grid_constant__ CUtensorMap rmap1) {
-    constexpr int SG = EPI == PC_EPI_GATE ? 4 : 8;          // 16-byte channel groups per plane of a staging tile (32 / 64 channels)
-    constexpr int STG = 2 * SG * 128 * 16;                   // bytes per slot: 16 KB / 32 KB
+    constexpr int SG = EPI == PC_EPI_GATE ? 4 : 8;          // 16-byte channel groups per plane of a chunk's output (32 / 64 channels)
+    constexpr int STG = EPI == PC_EPI_GATE ? 0 : 2 * SG * 128 * 16;      // staging bytes per slot (RS: 32 KB; GATE stores straight from registers)
     extern __shared__ __align__(128) uint8_t psm[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_max_sync(0xffffffffu, tid >> 5);
@@ -163,10 +181,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
     uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)p.nb * PC_STAGE);
     uint64_t* a_full = bars;             // [1]
     uint64_t* a_empty = bars + 1;        // [1]
-    uint64_t* m_full = bars + 2;         // [2]
-    uint64_t* m_empty = bars + 4;        // [2]
-    uint64_t* c_full = bars + 6;         // [2]
-    uint64_t* c_empty = bars + 8;        // [2]
+    uint64_t* acc_full = bars + 2;       // [slot][buffer]
+    uint64_t* acc_empty = bars + 6;      // [slot][buffer]
     uint64_t* r_full = bars + 10;        // [2] residual tile landed in the slot's staging buffer (RS)
     uint64_t* s_free = bars + 12;        // [2] staging buffer free again (its bulk stores have read it)
     uint64_t* b_full = bars + 14;        // [PC_MAX_RING]
@@ -175,11 +191,8 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
 
     if (tid == 0) {
         mbar_init(a_full, 1); mbar_init(a_empty, 4);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&m_full[i], 1); mbar_init(&m_empty[i], 8);
-            mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 8);
-            mbar_init(&r_full[i], 1); mbar_init(&s_free[i], 1);
-        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&r_full[i], 1); mbar_init(&s_free[i], 1); }
         for (int s = 0; s < PC_MAX_RING; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 2 * p.ncta); }    // both issuers of the slot, in every CTA of the cluster
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -191,42 +204,50 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;     // slot s: main @ s*192 (128 columns: hi*hi | hi*lo), corr @ s*192 + 128 (64 columns)
+    const uint32_t tmem = *tmem_slot;     // slot s, buffer b @ s*256 + b*128: 64 columns hi*hi | 64 columns hi*lo + lo*hi
     if (p.ncta == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
-    const int W = p.nclu_items, wstep = gridDim.x / p.ncta;
+    // contiguous range of (tile-major) cluster items: consecutive items share the activation tile, which is loaded once per tile
     const int crank = p.ncta == 2 ? (int)cluster_rank() : 0;
+    const int w0 = min(p.nclu_items, (int)(blockIdx.x / p.ncta) * p.per), w1 = min(p.nclu_items, w0 + p.per);
 
     if (warp < 16) {
         // ================= promotion + epilogue: (slot, column half hf), one row x 32 columns per thread ==================
         const int wq = warp & 3, slot = (warp >> 2) & 1, hf = warp >> 3;
         const int tl = wq * 32 + lane;
-        const uint32_t tmain = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * 192 + hf * 32);
-        const uint32_t tcorr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * 192 + 128 + hf * 32);
+        const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(slot * 256 + hf * 32);
         uint8_t* sbuf = stg + (size_t)slot * STG;
-        uint32_t mf_par = 0, cf_par = 0, rf_par = 0;
+        uint32_t f_par = 0, rf_par = 0;      // f_par: bit b = parity of acc_full[slot][b]
         float amax = 0.f;
         float racc[32];
-        const int SPU = p.mode ? (1 << 20) : max(1, p.usteps / 4);
-        const int NU = p.mode ? 1 : (p.nst + SPU - 1) / SPU;
-        int item = 0;
-        for (int w = blockIdx.x / p.ncta; w < W; w += wstep, ++item) {
+        const int SPU = max(1, p.usteps / 4);
+        const int NU = p.mode ? 2 : (p.nst + SPU - 1) / SPU;
+#pragma unroll 1
+        for (int w = w0; w < w1; ++w) {
             const int pair = w % p.npairs, ti = (w / p.npairs) * p.ncta + crank;
             const int chunk = pair * 2 + slot;
             const bool active = chunk < p.nchunks && ti < p.ntiles;
             if (!active) continue;                    // (the partner slot still runs; nothing of this slot's barriers is used)
             const RbTile it = rb_tile_at(p.seg, p.tiles, ti);
+#pragma unroll 1
             for (int un = 0; un < NU; ++un) {
-                mbar_wait_all(&m_full[slot], mf_par); mf_par ^= 1;
+                const int b = un & 1;
+                mbar_wait_all(&acc_full[slot * 2 + b], (f_par >> b) & 1u); f_par ^= 1u << b;
                 tc_fence_after();
+                const uint32_t tsrc = tbase + (uint32_t)(b * 128);
 #pragma unroll
                 for (int cb = 0; cb < 32; cb += 16) {
                     uint32_t v[16], x2[16];
-                    tc_ld_nowait<16>(tmain + cb, v);
-                    if (!p.mode) tc_ld_nowait<16>(tmain + 64 + cb, x2);
+                    tc_ld_nowait<16>(tsrc + cb, v);
+                    if (!p.mode) tc_ld_nowait<16>(tsrc + 64 + cb, x2);
                     tc_ld_wait();
                     if (p.mode) {
+                        if (un == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) racc[cb + j] = __uint_as_float(v[j]);
+                            for (int j = 0; j < 16; ++j) racc[cb + j] = __uint_as_float(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) racc[cb + j] += __uint_as_float(v[j]);
+                        }
                     } else if (un == 0) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) racc[cb + j] = __uint_as_float(v[j]) + __uint_as_float(x2[j]);
@@ -237,30 +258,14 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&m_empty[slot]);
-            }
-            {
-                mbar_wait_all(&c_full[slot], cf_par); cf_par ^= 1;
-                tc_fence_after();
-#pragma unroll
-                for (int cb = 0; cb < 32; cb += 16) {
-                    uint32_t v[16];
-                    tc_ld_nowait<16>(tcorr + cb, v);
-                    tc_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) racc[cb + j] += __uint_as_float(v[j]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&c_empty[slot]);
+                if (lane == 0) mbar_arrive(&acc_empty[slot * 2 + b]);
             }
             const int tr = it.t0 + tl;
             const bool valid = tr < it.len;
             const int n0 = chunk * PC_NCH + hf * 32;       // first output column of this thread
-            if (EPI == PC_EPI_GATE) {
-                // the previous item's bulk stores of this slot (issued by these same lanes) must have read the staging tile
-                if (tl < 2 * SG && hf == 0) bulk_wait_read0();
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+            if (EPI == PC_EPI_GATE && (p.dbg & 4)) {
+            } else if (EPI == PC_EPI_GATE) {
+                // acts planes straight from registers: lane = row, so every 16-byte store of a warp lands in 512 contiguous bytes
                 const float isc = p.isc;
                 float o[16];
 #pragma unroll
@@ -272,34 +277,26 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                     amax = fmaxf(amax, valid ? fabsf(g) : 0.f);
                     o[j] = g;
                 }
-#pragma unroll
-                for (int gg = 0; gg < 2; ++gg) {
-                    uint4 hi, lo;
-                    split8_scaled(o + 8 * gg, hi, lo);
-                    if (!valid) { hi = make_uint4(0, 0, 0, 0); lo = hi; }
-                    *reinterpret_cast<uint4*>(pc_cell(sbuf, SG, 0, hf * 2 + gg, tl)) = hi;
-                    *reinterpret_cast<uint4*>(pc_cell(sbuf, SG, 1, hf * 2 + gg, tl)) = lo;
-                }
-                fence_proxy_async();
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
-                if (tl < 2 * SG && hf == 0) {             // 8 bulk stores per chunk: (plane, group) x the valid rows
-                    const int plane = tl / SG, g = tl - plane * SG;
-                    const int nrows = min(128, it.len - it.t0);
+                if (valid) {                               // rows past the utterance stay untouched: the gap rows are zero, the next utterance is not ours
                     const int Gout = p.out0.C / 8;
-                    __half* gdst = p.out0.base + ((size_t)(plane * Gout + chunk * SG + g) * p.out0.rows_p + (size_t)(it.prow_u + it.t0)) * 8;
-                    bulk_s2g(gdst, pc_cell(sbuf, SG, plane, g, 0), (uint32_t)nrows * 16);
-                    bulk_commit();
+#pragma unroll
+                    for (int gg = 0; gg < 2; ++gg) {
+                        uint4 hi, lo;
+                        split8_scaled(o + 8 * gg, hi, lo);
+                        __half* dh = p.out0.base + ((size_t)(chunk * SG + hf * 2 + gg) * p.out0.rows_p + (size_t)(it.prow_u + tr)) * 8;
+                        *reinterpret_cast<uint4*>(dh) = hi;
+                        *reinterpret_cast<uint4*>(dh + (size_t)Gout * p.out0.rows_p * 8) = lo;
+                    }
                 }
             } else {
                 const bool to1 = chunk >= p.split;
                 const Planes& op = to1 ? p.out1 : p.out0;
                 const int oc = to1 ? chunk - p.split : chunk;          // 64-channel chunk inside the destination stream
                 const bool accin = to1 ? p.acc1 != 0 : p.acc0 != 0;
-                if (accin) { mbar_wait_all(&r_full[slot], rf_par); rf_par ^= 1; }
-                else {                                                  // nothing was loaded: the staging tile is written from scratch
-                    if (tl < 2 * SG && hf == 0) bulk_wait_read0();
-                    asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
-                }
+                // the producer hands the staging tile over once per chunk — with the stream's previous value in it when the chunk
+                // accumulates, empty otherwise — and only after the previous chunk's bulk stores have read it (s_free).  Waiting
+                // here in both cases keeps the epilogue from running a whole s_free phase ahead of the producer's parity test.
+                mbar_wait_all(&r_full[slot], rf_par); rf_par ^= 1;
                 const float isc8 = p.isc * TC_ASCALE;
 #pragma unroll
                 for (int gg = 0; gg < 4; ++gg) {
@@ -342,36 +339,38 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                 }
             }
         }
-        if (tl < 2 * SG && hf == 0) bulk_wait_all0();
-        if (amax > 65000.f && p.flags) atomicOr(p.flags, 1u);
+        if (EPI == PC_EPI_RS && tl < 2 * SG && hf == 0) bulk_wait_all0();
+        if (amax > 65000.f && p.flags && !p.dbg) atomicOr(p.flags, 1u);
     } else if (warp < 20) {
-        if (lane == 0) {
-            const int kind = (warp - 16) >> 1, islot = (warp - 16) & 1;
-            if (kind == 0) pc_issuer<0>(p, islot, smem_u32(abuf), smem_u32(wst), tmem, a_full, a_empty, m_full, m_empty, c_full, c_empty, b_full, b_empty);
-            else pc_issuer<1>(p, islot, smem_u32(abuf), smem_u32(wst), tmem, a_full, a_empty, m_full, m_empty, c_full, c_empty, b_full, b_empty);
-        }
+        if (lane == 0)
+            pc_issuer(p, (warp - 16) & 1, (warp - 16) >> 1, w0, w1, crank, smem_u32(abuf), smem_u32(wst), tmem, a_full, a_empty, acc_full, acc_empty, b_full,
+                      b_empty);
         __syncwarp();
     } else {
         // ================= producer: activation tiles, residual tiles (RS) and weight stages, one thread, cooperative polling ===
         if (lane == 0) {
-            int xw = blockIdx.x / p.ncta; uint32_t ae_par = 1;
-            int rw = blockIdx.x / p.ncta; uint32_t sf_par0 = 1, sf_par1 = 1; int rslot = 0;
-            int ww = blockIdx.x / p.ncta, wstage = 0, wq2 = 0, ws_ = 0; uint32_t wph = 1;
+            int xw = w0; uint32_t ae_par = 1;
+            int rw = w0; uint32_t sf_par0 = 1, sf_par1 = 1; int rslot = 0;
+            int ww = w0, wstage = 0, wq2 = 0, ws_ = 0; uint32_t wph = 1;
             const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
-            if (EPI != PC_EPI_RS) rw = W;
-            while (xw < W || ww < W || rw < W) {
+            if (EPI != PC_EPI_RS) rw = w1;
+            while (xw < w1 || ww < w1 || rw < w1) {
                 bool progress = false;
-                if (xw < W && (xw / p.npairs) * p.ncta + crank >= p.ntiles) { xw += wstep; progress = true; }      // odd tail: no tile for this CTA
-                else if (xw < W && mbar_test(a_empty, ae_par)) {
-                    ae_par ^= 1;
-                    const RbTile it = rb_tile_at(p.seg, p.tiles, (xw / p.npairs) * p.ncta + crank);
-                    const long long r0 = it.prow_u + it.t0 - p.padl;
-                    mbar_expect_tx(a_full, a_tile);
-                    tma_load_3d(abuf, &imap, 0, (int)r0, 0, a_full);
-                    xw += wstep;
-                    progress = true;
+                if (xw < w1) {                         // next activation tile: the first item of the next tile group of this range
+                    const int tg = xw / p.npairs, xti = tg * p.ncta + crank;
+                    if (xti >= p.ntiles) { xw = min(w1, (tg + 1) * p.npairs); progress = true; }       // odd tail: no tile for this CTA
+                    else if (mbar_test(a_empty, ae_par)) {
+                        ae_par ^= 1;
+                        const RbTile it = rb_tile_at(p.seg, p.tiles, xti);
+                        const long long r0 = it.prow_u + it.t0 - p.padl;
+                        mbar_expect_tx(a_full, a_tile);
+                        if (p.bulk_in) planes_tile_g2s(abuf, p.inp, 0, 2 * p.G, r0, p.xr, a_full);
+                        else tma_load_3d(abuf, &imap, 0, (int)r0, 0, a_full);
+                        xw = min(w1, (tg + 1) * p.npairs);
+                        progress = true;
+                    }
                 }
-                if (rw < W) {                          // residual tile of (item rw, slot rslot): hi groups, then lo groups
+                if (rw < w1) {                         // residual tile of (item rw, slot rslot): hi groups, then lo groups
                     const int chunk = (rw % p.npairs) * 2 + rslot;
                     const bool to1 = chunk >= p.split;
                     const int rti = (rw / p.npairs) * p.ncta + crank;
@@ -385,30 +384,39 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                         adv = true;
                         progress = true;
                     }
+                    if (act && adv && !need) mbar_arrive(&r_full[rslot]);          // staging tile free, nothing to load
                     if (act && adv && need) {
                         const RbTile it = rb_tile_at(p.seg, p.tiles, rti);
                         const Planes& op = to1 ? p.out1 : p.out0;
                         const int oc = to1 ? chunk - p.split : chunk;
-                        const CUtensorMap* rm = to1 ? &rmap1 : &rmap0;
                         uint8_t* dst = stg + (size_t)rslot * STG;
                         mbar_expect_tx(&r_full[rslot], STG);
-                        tma_load_3d(dst, rm, 0, (int)(it.prow_u + it.t0), oc * SG, &r_full[rslot]);
-                        tma_load_3d(dst + STG / 2, rm, 0, (int)(it.prow_u + it.t0), op.C / 8 + oc * SG, &r_full[rslot]);
+                        if (p.bulk_in) {
+                            planes_tile_g2s(dst, op, oc * SG, SG, it.prow_u + it.t0, 128, &r_full[rslot]);
+                            planes_tile_g2s(dst + STG / 2, op, op.C / 8 + oc * SG, SG, it.prow_u + it.t0, 128, &r_full[rslot]);
+                        } else {
+                            const CUtensorMap* rm = to1 ? &rmap1 : &rmap0;
+                            tma_load_3d(dst, rm, 0, (int)(it.prow_u + it.t0), oc * SG, &r_full[rslot]);
+                            tma_load_3d(dst + STG / 2, rm, 0, (int)(it.prow_u + it.t0), op.C / 8 + oc * SG, &r_full[rslot]);
+                        }
                     }
-                    if (adv) { if (++rslot == 2) { rslot = 0; rw += wstep; } }
+                    if (adv) { if (++rslot == 2) { rslot = 0; ++rw; } }
                 }
-                if (ww < W && mbar_test(&b_empty[ws_], wph)) {
+                if (ww < w1 && mbar_test(&b_empty[ws_], wph)) {
                     // ring order: stage 0 of slot 0, stage 0 of slot 1, stage 1 of slot 0, ...
                     const int chunk = (ww % p.npairs) * 2 + wq2;
                     const int cc = min(chunk, p.nchunks - 1);          // an inactive slot still gets (ignored) bytes: keeps the ring walk uniform
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + ((size_t)cc * p.nst + wstage) * PC_STAGE;
+                    if (p.dbg & 1) mbar_arrive(&b_full[ws_]);
+                    else {
                     mbar_expect_tx(&b_full[ws_], PC_STAGE);
                     if (p.ncta == 2) {        // this CTA fetches its half of the stage and multicasts it into both CTAs (same offsets, same barrier)
                         const uint32_t half = PC_STAGE / 2;
                         bulk_g2s_mc(wst + (size_t)ws_ * PC_STAGE + crank * half, src + crank * half, half, &b_full[ws_], mc_mask);
                     } else bulk_g2s(wst + (size_t)ws_ * PC_STAGE, src, PC_STAGE, &b_full[ws_]);
+                    }
                     if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
-                    if (++wq2 == 2) { wq2 = 0; if (++wstage == p.nst) { wstage = 0; ww += wstep; } }
+                    if (++wq2 == 2) { wq2 = 0; if (++wstage == p.nst) { wstage = 0; ++ww; } }
                     progress = true;
                 }
                 if (!progress) __nanosleep(32);
@@ -471,7 +479,7 @@ inline PcPlan pc_plan(const PcWeights& w, int epi) {
     PcPlan pl;
     const size_t xr = 128 + (size_t)(w.k - 1) * w.dil;
     const size_t a_tile = (size_t)(w.Cin / 8) * 2 * xr * 16;
-    const size_t stg = (size_t)2 * (epi == PC_EPI_GATE ? 16 : 32) * 1024;
+    const size_t stg = epi == PC_EPI_GATE ? 0 : (size_t)2 * 32 * 1024;      // GATE stores straight from registers
     const size_t misc = (14 + 2 * PC_MAX_RING) * 8 + 64;
     const size_t budget = 225 * 1024;
     size_t room = budget > a_tile + stg + misc ? (budget - a_tile - stg - misc) / PC_STAGE : 0;
@@ -556,9 +564,30 @@ inline int pc_launch(int epi, const PcWeights& w, const Planes& in, const Planes
         static int left2 = 4;
         if (left2 > 0) { --left2; fprintf(stderr, "pc_conv: cluster %d, grid %d, cluster items %d\n", p.ncta, ctas, p.nclu_items); }
     }
+    p.per = (p.nclu_items + ctas / p.ncta - 1) / (ctas / p.ncta);
+    static const int env_tile_tma = getenv("STTS_TILE_TMA") ? atoi(getenv("STTS_TILE_TMA")) : 0;
+    p.inp = in; p.bulk_in = env_tile_tma ? 0 : 1;
+    static const int env_dbg = getenv("STTS_PC_DBG") ? atoi(getenv("STTS_PC_DBG")) : 0;
+    p.dbg = epi == PC_EPI_GATE ? env_dbg : 0;
+    static long long* trace_buf = nullptr;
+    static const int env_trace = getenv("STTS_PC_TRACE") ? atoi(getenv("STTS_PC_TRACE")) : 0;
+    static int trace_left[2] = {2, 2};
+    const bool do_trace = env_trace && trace_left[epi] > 0 && ntiles > 100;
+    if (do_trace && !trace_buf) cudaMalloc(&trace_buf, 64 * 8);
+    if (do_trace) cudaMemsetAsync(trace_buf, 0, 64 * 8, stream);
+    p.trace = do_trace ? trace_buf : nullptr;
     cudaError_t le;
     if (epi == PC_EPI_GATE) le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_GATE>, p, imap, rmap0, rmap1);
     else le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_RS>, p, imap, rmap0, rmap1);
+    if (do_trace) {
+        --trace_left[epi];
+        long long h[64];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "PCTRACE epi=%d mode=%d items/cta %d nb=%d:", epi, mode, p.per, p.nb);
+        for (int r = 0; r < 4; ++r) fprintf(stderr, "  [buf%d slot%d total %lld a_full %lld empty %lld b_full %lld]", r >> 1, r & 1, h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
+        fprintf(stderr, "\n");
+    }
     return le == cudaSuccess ? 1 : -5;
 }
 

@@ -56,6 +56,7 @@ struct RbP {
     float in_slope;                  // input planes hold leaky(x): residual x = v < 0 ? v / in_slope : v   (0: identity)
     int out_act; float out_slope;
     int tmem_cols;
+    Planes inp; int bulk_in;         // input planes; 1: x tiles by 1-D bulk copies (planes_tile_g2s), 0: tensor-map boxes (STTS_TILE_TMA=1)
     Planes outp;                     // destination planes (written with 1-D bulk stores of the exact valid rows)
     unsigned int* flags;             // bit 0: an activation exceeded the fp16 range of the split (|8 x| > 65504)
     int dbg;                         // experiments (STTS_RB_DBG): bit 0 = epilogue / producer mbarrier polls back off with nanosleep
@@ -540,8 +541,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                         const RbTile it = rb_tile(p, xw);
                         const long long r0 = it.prow_u + it.t0 - p.pad2 - p.pad1;      // >= prow_u - TC_GAP >= 0
                         mbar_expect_tx(&a_full[buf], 2 * a_tile);
-                        tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
-                        tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
+                        if (p.bulk_in) {
+                            planes_tile_g2s(abuf + (size_t)(buf * 2 + 0) * a_tile, p.inp, 0, 2 * (C / 8), r0, p.xr1, &a_full[buf]);
+                            planes_tile_g2s(abuf + (size_t)(buf * 2 + 1) * a_tile, p.inp, 0, 2 * (C / 8), r0 + 128, p.xr1, &a_full[buf]);
+                        } else {
+                            tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
+                            tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
+                        }
                         xw += wstep; ++xtile;
                         progress = true;
                     }
@@ -742,6 +748,8 @@ inline int rb_pair_launch(int C, const RbWeights& a, const RbWeights& b, const P
     p.tiles = tiles; p.work_items = ntiles;
     alignas(64) CUtensorMap imap;
     if (!rb_make_map(&imap, in, p.xr1)) return -1;
+    static const int env_tile_tma = getenv("STTS_TILE_TMA") ? atoi(getenv("STTS_TILE_TMA")) : 0;
+    p.inp = in; p.bulk_in = env_tile_tma ? 0 : 1;
     p.outp = out;
     static const int env_grid = getenv("STTS_RB_GRID") ? atoi(getenv("STTS_RB_GRID")) : 0;
     int ctas = env_grid > 0 ? env_grid : sms;
