@@ -1126,12 +1126,11 @@ void stts_engine::run() {
         for (auto& c : L.rs) flowTc = flowTc && tc_layer(c);
     }
     if (flowTc) { hP = arena_planes(Ft, B, WH); actsP = arena_planes(Ft, B, WH); skipP = arena_planes(Ft, B, WH); }
-    // WaveNet layers on the staged-epilogue wide conv (pc_fused.cuh): h and skip live as planes only
-    // STTS_PC_FUSED bit 0: res_skip, bit 1: in_layer.  Measured (1xB200, 64 x 640 frames): res_skip 107 -> 74 us per launch on
-    // the staged-epilogue kernel; the k5 in_layer is bound by the depth of its weight ring there (64 KB beside a 101 KB activation
-    // tile: 195 us vs 142 us for conv_tc's column-split tiles), so by default it stays on conv_tc except in throughput mode.
+    // WaveNet layers on pc_fused.cuh (activation tile resident per row tile, weights streamed): h and skip live as planes only.
+    // STTS_PC_FUSED bit 0: res_skip, bit 1: in_layer (default 3: both).  Measured per launch (1xB200, 64 x 640 frames, accurate
+    // mode): res_skip 107 us (conv_tc) -> 45 us, in_layer 142 us (conv_tc column-split tiles) -> 115 us; throughput mode 73 us.
     static const int env_pc = getenv("STTS_PC_FUSED") ? atoi(getenv("STTS_PC_FUSED")) : -1;
-    const int pc_bits = env_pc >= 0 ? env_pc : (tensor_mode == 2 ? 3 : 1);
+    const int pc_bits = env_pc >= 0 ? env_pc : 3;
     bool flowPc = flowTc && pc_bits != 0;
     for (auto& L : flow) {
         for (auto& c : L.in) flowPc = flowPc && pc_eligible(c.pc, PC_EPI_GATE) && c.Cout == 2 * WH && c.Cin == WH;

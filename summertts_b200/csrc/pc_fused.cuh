@@ -23,7 +23,7 @@
 
 namespace stts {
 
-constexpr int PC_THREADS = 672;     // warps 0-15: epilogue sets (slot x column half x lane quarter); 16-19: issuers (slot x accumulator buffer); 20: producer
+constexpr int PC_THREADS = 704;     // warps 0-15: epilogue sets (slot x column half x lane quarter); 16-19: issuers (slot x accumulator buffer); 20: weight producer; 21: tile producer
 constexpr int PC_NCH = 64;          // output columns per chunk
 constexpr int PC_KC = 64;           // input channels per weight stage
 constexpr int PC_STAGE = PC_KC * 2 * PC_NCH * 2;    // 16 KB
@@ -75,14 +75,7 @@ __device__ __forceinline__ uint8_t* pc_cell(uint8_t* stg, int groups, int plane,
     return stg + ((size_t)(plane * groups + g) * 128 + r) * 16;
 }
 
-// ring entry `e` (0 .. 2 nst - 1: stage-major, slot-minor) of an item whose first entry sits at (base_slot, base_ph)
-__device__ __forceinline__ void pc_ring_at(int base_slot, uint32_t base_ph, int e, int nb, int& slot_r, uint32_t& ph_r) {
-    const int q = base_slot + e, wrap = q / nb;
-    slot_r = q - wrap * nb;
-    ph_r = base_ph ^ (uint32_t)(wrap & 1);
-}
-
-// MMA issuer (slot, b): every promotion unit u = b (mod 2) of the slot's chunk goes into accumulator buffer b — main product
+// MMA issuer warp (slot, b) — the whole warp runs this, one elected lane issues: every promotion unit u = b (mod 2) of the slot's chunk goes into accumulator buffer b — main product
 // A_hi x [W_hi | W_lo] (N = 128) and correction A_lo x W_hi (N = 64, accumulated onto the hi*lo half) from the SAME thread, so
 // their order in the tensor pipe is the program order.  The two issuers of a slot alternate units: while buffer b drains, the
 // other buffer's MMAs run.  Throughput mode: ONE N = 64 MMA per K-step, issuer b takes the stages st = b (mod 2), no promotion.
@@ -107,39 +100,45 @@ __device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const in
     const int kcs = p.G / 8;                                        // 64-channel blocks per tap
     const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
     uint32_t af_par = 0, e_par = 1;
-    int rs0 = 0; uint32_t rp0 = 0;                                  // ring position of the item's first entry
+    int rs0 = slot; uint32_t rp0 = 0;                               // ring slot / phase of this chunk slot's next entry
     int prev_tg = -1;
 #ifdef STTS_TC_TRACE_BUILD
+    long long* tl_ = (p.trace && blockIdx.x == 0 && slot == 0) ? p.trace + 64 + b * 512 : nullptr; int titem = 0;
+#define PC_TL(st, k) do { if (tl_ && titem < 8 && (threadIdx.x & 31) == 0) tl_[(titem * 15 + (st)) * 4 + (k)] = clock64(); } while (0)
     long long t_a = 0, t_e = 0, t_b = 0, t_all = clock64(), tt;
 #define PC_T0() tt = clock64()
 #define PC_T1(acc) acc += clock64() - tt
 #else
 #define PC_T0()
 #define PC_T1(acc)
+#define PC_TL(st, k)
 #endif
 #pragma unroll 1
     for (int w = w0; w < w1; ++w) {
         const int pair = w % p.npairs, tg = w / p.npairs, ti = tg * p.ncta + rank;
         const bool has_tile = ti < p.ntiles;                        // (a cluster's odd tail: only the weight-stage protocol runs)
         const bool active = has_tile && pair * 2 + slot < p.nchunks;
-        if (has_tile && tg != prev_tg) { PC_T0(); mbar_wait(a_full, af_par); af_par ^= 1; PC_T1(t_a); tc_fence_after(); }
+        if (has_tile && tg != prev_tg) { PC_T0(); mbar_wait_warp(a_full, af_par); af_par ^= 1; PC_T1(t_a); tc_fence_after(); }
         prev_tg = tg;
         // Both issuers of the slot walk EVERY stage of the slot's chunk and wait for its weights, whoever owns the stage: a ring
         // entry is refilled only after both have passed it, so neither can fall a whole mbarrier phase behind a ring slot
         // (a parity wait cannot tell fill n from fill n + 2).
         uint32_t acc = 0u;
+        int tap = 0, kc = 0, uin = 0, ub = 0;                       // tap / 64-channel block of the stage; stage within its unit; unit parity
 #pragma unroll 1
         for (int st = 0; st < nst; ++st) {
-            const bool own = mode ? ((st & 1) == b) : (((st / SPU) & 1) == b);
-            const bool first = mode ? (st == b) : (st % SPU == 0);
-            const bool last = mode ? (st + 2 >= nst) : (st % SPU == SPU - 1 || st == nst - 1);
-            if (own && active && first) { PC_T0(); mbar_wait(empty_bar, e_par); e_par ^= 1; PC_T1(t_e); tc_fence_after(); acc = 0u; }
-            int slot_r; uint32_t ph_r;
-            pc_ring_at(rs0, rp0, 2 * st + slot, nb, slot_r, ph_r);
-            PC_T0(); mbar_wait(&b_full[slot_r], ph_r); PC_T1(t_b);
+            const bool own = mode ? ((st & 1) == b) : (ub == b);
+            const bool first = mode ? (st == b) : (uin == 0);
+            const bool last = mode ? (st + 2 >= nst) : (uin == SPU - 1 || st == nst - 1);
+            if (own && active && first) { PC_T0(); mbar_wait_warp(empty_bar, e_par); e_par ^= 1; PC_T1(t_e); tc_fence_after(); acc = 0u; }
+            const int slot_r = rs0; const uint32_t ph_r = rp0;      // this slot's entries are every second ring entry, items back to back
+            rs0 += 2; if (rs0 >= nb) { rs0 -= nb; rp0 ^= 1u; }
+            PC_TL(st, 0);
+            PC_T0(); mbar_wait_warp(&b_full[slot_r], ph_r); PC_T1(t_b);
             tc_fence_after();
+            PC_TL(st, 1);
+            if (elect_one()) {      // one election per stage: the MMAs and the commits that track them come from the same thread
             if (own && active && !(p.dbg & 2)) {
-                const int tap = st / kcs, kc = st - tap * kcs;
                 const uint64_t da = a_bits | (uint64_t)(((a_s0 + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(kc * 8) * a_lbo) & 0x3FFFFu) >> 4);
                 const uint64_t dl = a_bits | (uint64_t)(((a_s0 + a_lo + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(kc * 8) * a_lbo) & 0x3FFFFu) >> 4);
                 const uint64_t db = b_desc0 + (uint32_t)slot_r * (uint32_t)(PC_STAGE >> 4);
@@ -157,12 +156,19 @@ __device__ __forceinline__ void pc_issuer(const PcP& p, const int slot, const in
             }
             if (p.ncta == 2) tc_commit_mc(&b_empty[slot_r], mc_mask); else tc_commit(&b_empty[slot_r]);
             if (own && active && last) tc_commit(full_bar);
+            }
+            PC_TL(st, 3);
+            if (++kc == kcs) { kc = 0; ++tap; }
+            if (++uin == SPU) { uin = 0; ub ^= 1; }
         }
-        { int s2; uint32_t p2; pc_ring_at(rs0, rp0, 2 * nst, nb, s2, p2); rs0 = s2; rp0 = p2; }
-        if (has_tile && (w + 1 == w1 || (w + 1) / p.npairs != tg)) tc_commit(a_empty);   // this issuer's reads of the activation tile have retired
+#ifdef STTS_TC_TRACE_BUILD
+        ++titem;
+#endif
+        if (has_tile && (w + 1 == w1 || (w + 1) / p.npairs != tg)) { if (elect_one()) tc_commit(a_empty); }   // this issuer's reads of the activation tile have retired
+        __syncwarp();
     }
 #ifdef STTS_TC_TRACE_BUILD
-    if (p.trace && blockIdx.x == 0) { long long* o = p.trace + (b * 2 + slot) * 8; o[0] = clock64() - t_all; o[1] = t_a; o[2] = t_e; o[3] = t_b; }
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) { long long* o = p.trace + (b * 2 + slot) * 8; o[0] = clock64() - t_all; o[1] = t_a; o[2] = t_e; o[3] = t_b; }
 #endif
 }
 
@@ -221,6 +227,12 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
         float racc[32];
         const int SPU = max(1, p.usteps / 4);
         const int NU = p.mode ? 2 : (p.nst + SPU - 1) / SPU;
+#ifdef STTS_TC_TRACE_BUILD
+        long long* el_ = (p.trace && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.trace + 64 + 1024 : nullptr; int eitem = 0;
+#define PC_EL(un, k) do { if (el_ && eitem < 8) el_[(eitem * 9 + (un)) * 3 + (k)] = clock64(); } while (0)
+#else
+#define PC_EL(un, k)
+#endif
 #pragma unroll 1
         for (int w = w0; w < w1; ++w) {
             const int pair = w % p.npairs, ti = (w / p.npairs) * p.ncta + crank;
@@ -231,8 +243,10 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
 #pragma unroll 1
             for (int un = 0; un < NU; ++un) {
                 const int b = un & 1;
+                PC_EL(un, 0);
                 mbar_wait_all(&acc_full[slot * 2 + b], (f_par >> b) & 1u); f_par ^= 1u << b;
                 tc_fence_after();
+                PC_EL(un, 1);
                 const uint32_t tsrc = tbase + (uint32_t)(b * 128);
 #pragma unroll
                 for (int cb = 0; cb < 32; cb += 16) {
@@ -259,7 +273,9 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[slot * 2 + b]);
+                PC_EL(un, 2);
             }
+            PC_EL(8, 0);
             const int tr = it.t0 + tl;
             const bool valid = tr < it.len;
             const int n0 = chunk * PC_NCH + hf * 32;       // first output column of this thread
@@ -338,89 +354,120 @@ __global__ void __launch_bounds__(PC_THREADS, 1) pc_kernel(const PcP p, const __
                     if (lane == 0) mbar_arrive(&s_free[slot]);
                 }
             }
+            PC_EL(8, 1);
+#ifdef STTS_TC_TRACE_BUILD
+            ++eitem;
+#endif
         }
         if (EPI == PC_EPI_RS && tl < 2 * SG && hf == 0) bulk_wait_all0();
         if (amax > 65000.f && p.flags && !p.dbg) atomicOr(p.flags, 1u);
     } else if (warp < 20) {
-        if (lane == 0)
-            pc_issuer(p, (warp - 16) & 1, (warp - 16) >> 1, w0, w1, crank, smem_u32(abuf), smem_u32(wst), tmem, a_full, a_empty, acc_full, acc_empty, b_full,
-                      b_empty);
+        // the whole warp runs the issuer loop (warp-uniform control flow keeps the descriptors in uniform registers); one elected
+        // lane issues the MMAs and commits
+        pc_issuer(p, (warp - 16) & 1, (warp - 16) >> 1, w0, w1, crank, smem_u32(abuf), smem_u32(wst), tmem, a_full, a_empty, acc_full, acc_empty, b_full,
+                  b_empty);
         __syncwarp();
-    } else {
-        // ================= producer: activation tiles, residual tiles (RS) and weight stages, one thread, cooperative polling ===
+    } else if (warp == 20) {
+        // ================= weight producer: one thread, a tight blocking loop (a few instructions per 16 KB stage) ==============
+        // (A single thread polling all three streams cooperatively paced the whole kernel: ~100 dependent instructions per stage,
+        //  each ~10 cycles on an SM whose schedulers are shared with 16 polling epilogue warps — 1.2k cycles per stage, measured.)
         if (lane == 0) {
-            int xw = w0; uint32_t ae_par = 1;
-            int rw = w0; uint32_t sf_par0 = 1, sf_par1 = 1; int rslot = 0;
-            int ww = w0, wstage = 0, wq2 = 0, ws_ = 0; uint32_t wph = 1;
             const uint16_t mc_mask = (uint16_t)((1u << p.ncta) - 1u);
-            if (EPI != PC_EPI_RS) rw = w1;
-            while (xw < w1 || ww < w1 || rw < w1) {
-                bool progress = false;
-                if (xw < w1) {                         // next activation tile: the first item of the next tile group of this range
-                    const int tg = xw / p.npairs, xti = tg * p.ncta + crank;
-                    if (xti >= p.ntiles) { xw = min(w1, (tg + 1) * p.npairs); progress = true; }       // odd tail: no tile for this CTA
-                    else if (mbar_test(a_empty, ae_par)) {
-                        ae_par ^= 1;
-                        const RbTile it = rb_tile_at(p.seg, p.tiles, xti);
-                        const long long r0 = it.prow_u + it.t0 - p.padl;
-                        mbar_expect_tx(a_full, a_tile);
-                        if (p.bulk_in) planes_tile_g2s(abuf, p.inp, 0, 2 * p.G, r0, p.xr, a_full);
-                        else tma_load_3d(abuf, &imap, 0, (int)r0, 0, a_full);
-                        xw = min(w1, (tg + 1) * p.npairs);
-                        progress = true;
+            int ws_ = 0; uint32_t wph = 1;
+            int pair = w0 % p.npairs;
+#ifdef STTS_TC_TRACE_BUILD
+            int pfill = 0;
+            if (p.trace && blockIdx.x == 0) p.trace[63] = clock64();
+#endif
+#pragma unroll 1
+            for (int w = w0; w < w1; ++w) {
+                // ring order: stage 0 of slot 0, stage 0 of slot 1, stage 1 of slot 0, ...; an inactive slot (odd chunk count) still gets
+                // (ignored) bytes: the ring walk stays uniform
+                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.w) + (size_t)min(pair * 2, p.nchunks - 1) * p.nst * PC_STAGE;
+                const uint8_t* src1 = reinterpret_cast<const uint8_t*>(p.w) + (size_t)min(pair * 2 + 1, p.nchunks - 1) * p.nst * PC_STAGE;
+#pragma unroll 1
+                for (int st = 0; st < p.nst; ++st) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint8_t* src = (q ? src1 : src0) + (size_t)st * PC_STAGE;
+                        mbar_wait(&b_empty[ws_], wph);
+#ifdef STTS_TC_TRACE_BUILD
+                        if (p.trace && blockIdx.x == 0 && pfill < 256) p.trace[64 + 1024 + 256 + pfill] = clock64();
+                        ++pfill;
+#endif
+                        if (p.dbg & 1) mbar_arrive(&b_full[ws_]);
+                        else {
+                            mbar_expect_tx(&b_full[ws_], PC_STAGE);
+                            if (p.ncta == 2) {        // this CTA fetches its half of the stage and multicasts it into both CTAs (same offsets, same barrier)
+                                const uint32_t half = PC_STAGE / 2;
+                                bulk_g2s_mc(wst + (size_t)ws_ * PC_STAGE + crank * half, src + crank * half, half, &b_full[ws_], mc_mask);
+                            } else bulk_g2s(wst + (size_t)ws_ * PC_STAGE, src, PC_STAGE, &b_full[ws_]);
+                        }
+                        if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
                     }
                 }
-                if (rw < w1) {                         // residual tile of (item rw, slot rslot): hi groups, then lo groups
-                    const int chunk = (rw % p.npairs) * 2 + rslot;
-                    const bool to1 = chunk >= p.split;
-                    const int rti = (rw / p.npairs) * p.ncta + crank;
-                    const bool act = chunk < p.nchunks && rti < p.ntiles;
-                    const bool need = act && (to1 ? p.acc1 != 0 : p.acc0 != 0);
-                    bool adv = !act;
-                    // every active chunk's epilogue frees the staging tile once (s_free); the producer consumes each of those
-                    // completions, loading the stream's previous value when the chunk accumulates
-                    if (act && mbar_test(&s_free[rslot], rslot ? sf_par1 : sf_par0)) {
-                        if (rslot) sf_par1 ^= 1; else sf_par0 ^= 1;
-                        adv = true;
-                        progress = true;
-                    }
-                    if (act && adv && !need) mbar_arrive(&r_full[rslot]);          // staging tile free, nothing to load
-                    if (act && adv && need) {
-                        const RbTile it = rb_tile_at(p.seg, p.tiles, rti);
+                if (++pair == p.npairs) pair = 0;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= tile producer (warp 21): activation tiles and, for RS, the residual tiles, in item order ============
+        // Lane 0 waits (blocking) and posts the expected bytes; all lanes then issue the per-(plane, group) bulk copies of the tile.
+        // Order per item: [first item of a tile: a_empty -> activation tile]  slot 0 residual  slot 1 residual.  Everything a wait
+        // here depends on (the issuers' a_empty, the epilogue's s_free) needs only loads that come EARLIER in this sequence.
+        uint32_t ae_par = 1, sf_par0 = 1, sf_par1 = 1;
+        int pair = w0 % p.npairs, tg = w0 / p.npairs, prev_tg = -1;
+#pragma unroll 1
+        for (int w = w0; w < w1; ++w) {
+            const int ti = tg * p.ncta + crank;
+            const bool has_tile = ti < p.ntiles;       // (odd tail of a cluster: no tile for this CTA)
+            if (has_tile) {
+                const RbTile it = rb_tile_at(p.seg, p.tiles, ti);
+                if (tg != prev_tg) {
+                    if (lane == 0) { mbar_wait(a_empty, ae_par); mbar_expect_tx(a_full, a_tile); }
+                    ae_par ^= 1;
+                    __syncwarp();
+                    const long long r0 = it.prow_u + it.t0 - p.padl;
+                    if (p.bulk_in) {
+                        for (int g = lane; g < 2 * p.G; g += 32) planes_tile_g2s(abuf + (size_t)g * p.xr * 16, p.inp, g, 1, r0, p.xr, a_full);
+                    } else if (lane == 0) tma_load_3d(abuf, &imap, 0, (int)r0, 0, a_full);
+                }
+                if (EPI == PC_EPI_RS) {
+#pragma unroll
+                    for (int rslot = 0; rslot < 2; ++rslot) {
+                        const int chunk = pair * 2 + rslot;
+                        if (chunk >= p.nchunks) continue;
+                        const bool to1 = chunk >= p.split;
+                        const bool need = to1 ? p.acc1 != 0 : p.acc0 != 0;
                         const Planes& op = to1 ? p.out1 : p.out0;
                         const int oc = to1 ? chunk - p.split : chunk;
                         uint8_t* dst = stg + (size_t)rslot * STG;
-                        mbar_expect_tx(&r_full[rslot], STG);
-                        if (p.bulk_in) {
-                            planes_tile_g2s(dst, op, oc * SG, SG, it.prow_u + it.t0, 128, &r_full[rslot]);
-                            planes_tile_g2s(dst + STG / 2, op, op.C / 8 + oc * SG, SG, it.prow_u + it.t0, 128, &r_full[rslot]);
-                        } else {
-                            const CUtensorMap* rm = to1 ? &rmap1 : &rmap0;
-                            tma_load_3d(dst, rm, 0, (int)(it.prow_u + it.t0), oc * SG, &r_full[rslot]);
-                            tma_load_3d(dst + STG / 2, rm, 0, (int)(it.prow_u + it.t0), op.C / 8 + oc * SG, &r_full[rslot]);
+                        // every chunk's epilogue frees the staging tile once (s_free) and waits for it once (r_full): the stream's
+                        // previous value is loaded when the chunk accumulates, otherwise the tile is handed over empty
+                        if (lane == 0) {
+                            mbar_wait(&s_free[rslot], rslot ? sf_par1 : sf_par0);
+                            if (need) mbar_expect_tx(&r_full[rslot], STG); else mbar_arrive(&r_full[rslot]);
+                        }
+                        if (rslot) sf_par1 ^= 1; else sf_par0 ^= 1;
+                        __syncwarp();
+                        if (need) {
+                            const long long row = it.prow_u + it.t0;
+                            if (p.bulk_in) {
+                                if (lane < 2 * SG) {
+                                    const int plane = lane / SG, g = lane - plane * SG;
+                                    planes_tile_g2s(dst + (size_t)plane * (STG / 2) + (size_t)g * 128 * 16, op, plane * (op.C / 8) + oc * SG + g, 1, row, 128, &r_full[rslot]);
+                                }
+                            } else if (lane == 0) {
+                                const CUtensorMap* rm = to1 ? &rmap1 : &rmap0;
+                                tma_load_3d(dst, rm, 0, (int)row, oc * SG, &r_full[rslot]);
+                                tma_load_3d(dst + STG / 2, rm, 0, (int)row, op.C / 8 + oc * SG, &r_full[rslot]);
+                            }
                         }
                     }
-                    if (adv) { if (++rslot == 2) { rslot = 0; ++rw; } }
                 }
-                if (ww < w1 && mbar_test(&b_empty[ws_], wph)) {
-                    // ring order: stage 0 of slot 0, stage 0 of slot 1, stage 1 of slot 0, ...
-                    const int chunk = (ww % p.npairs) * 2 + wq2;
-                    const int cc = min(chunk, p.nchunks - 1);          // an inactive slot still gets (ignored) bytes: keeps the ring walk uniform
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + ((size_t)cc * p.nst + wstage) * PC_STAGE;
-                    if (p.dbg & 1) mbar_arrive(&b_full[ws_]);
-                    else {
-                    mbar_expect_tx(&b_full[ws_], PC_STAGE);
-                    if (p.ncta == 2) {        // this CTA fetches its half of the stage and multicasts it into both CTAs (same offsets, same barrier)
-                        const uint32_t half = PC_STAGE / 2;
-                        bulk_g2s_mc(wst + (size_t)ws_ * PC_STAGE + crank * half, src + crank * half, half, &b_full[ws_], mc_mask);
-                    } else bulk_g2s(wst + (size_t)ws_ * PC_STAGE, src, PC_STAGE, &b_full[ws_]);
-                    }
-                    if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
-                    if (++wq2 == 2) { wq2 = 0; if (++wstage == p.nst) { wstage = 0; ++ww; } }
-                    progress = true;
-                }
-                if (!progress) __nanosleep(32);
             }
+            prev_tg = tg;
+            if (++pair == p.npairs) { pair = 0; ++tg; }
         }
         __syncwarp();
     }
@@ -573,17 +620,21 @@ inline int pc_launch(int epi, const PcWeights& w, const Planes& in, const Planes
     static const int env_trace = getenv("STTS_PC_TRACE") ? atoi(getenv("STTS_PC_TRACE")) : 0;
     static int trace_left[2] = {2, 2};
     const bool do_trace = env_trace && trace_left[epi] > 0 && ntiles > 100;
-    if (do_trace && !trace_buf) cudaMalloc(&trace_buf, 64 * 8);
-    if (do_trace) cudaMemsetAsync(trace_buf, 0, 64 * 8, stream);
+    if (do_trace && !trace_buf) cudaMalloc(&trace_buf, 2048 * 8);
+    if (do_trace) cudaMemsetAsync(trace_buf, 0, 2048 * 8, stream);
     p.trace = do_trace ? trace_buf : nullptr;
     cudaError_t le;
     if (epi == PC_EPI_GATE) le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_GATE>, p, imap, rmap0, rmap1);
     else le = cudaLaunchKernelEx(&cfg, pc_kernel<PC_EPI_RS>, p, imap, rmap0, rmap1);
     if (do_trace) {
         --trace_left[epi];
-        long long h[64];
+        static long long h[2048];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        if (const char* tf = getenv("STTS_PC_TRACE_FILE")) {
+            char nm[512]; snprintf(nm, sizeof(nm), "%s.epi%d.%d", tf, epi, trace_left[epi]);
+            if (FILE* f = fopen(nm, "w")) { for (int i = 0; i < 2048; ++i) fprintf(f, "%lld\n", h[i]); fclose(f); }
+        }
         fprintf(stderr, "PCTRACE epi=%d mode=%d items/cta %d nb=%d:", epi, mode, p.per, p.nb);
         for (int r = 0; r < 4; ++r) fprintf(stderr, "  [buf%d slot%d total %lld a_full %lld empty %lld b_full %lld]", r >> 1, r & 1, h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3]);
         fprintf(stderr, "\n");

@@ -28,7 +28,7 @@
 
 namespace stts {
 
-constexpr int RB_THREADS = 672;     // warps 0-15: four epilogue sets (M-tile x column half); 16-19: MMA issuers (kind x M-tile); 20: producer (x tiles + weights)
+constexpr int RB_THREADS = 704;     // warps 0-15: four epilogue sets (M-tile x column half); 16-19: MMA issuers (kind x M-tile); 20: weight producer; 21: x-tile producer
 constexpr int RB_MAX_STAGES = 32;   // weight stages (taps of conv1 + conv2) when resident; ring depth otherwise
 
 struct RbWeights {                  // one conv of the pair, merged split-fp16 stages [tap][C/8][hi rows C | lo rows C][8]
@@ -514,14 +514,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
             else rb_issuer<C, 1>(p, imt, smem_u32(abuf), smem_u32(t1), smem_u32(wst), tmem, a_full, m_full, m_empty, c_full, c_empty, t1_full, b_full, b_empty, rtr);
         }
         __syncwarp();
-    } else {
-        // ================= producer: ONE thread feeds both the x tiles (TMA) and the weight stages (bulk copies) ==========
-        // cooperative polling (mbarrier.test_wait, never blocking on one stream while the other could advance)
+    } else if (warp == 20) {
+        // ================= weight producer: one thread, blocking loop (resident: every stage once; else the ring) ==========
+        // (One thread polling both streams cooperatively costs ~100 dependent instructions per stage — pc_fused.cuh measured
+        //  1.2k cycles per stage for that pattern; two simple blocking loops in two warps cost a few dozen.)
         if (lane == 0) {
-            // x tiles
-            int xw = blockIdx.x, xtile = 0; uint32_t ae_par0 = 1, ae_par1 = 1;
-            // weights
-            int ww = blockIdx.x, wc = 0, wtap = 0, ws_ = 0; uint32_t wph = 1;
             if (p.resident) {
                 if ((int)blockIdx.x < W)
                     for (int s2 = 0; s2 < p.k1 + p.k2; ++s2) {
@@ -530,39 +527,44 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_pair_kernel(const RbP p, con
                         mbar_expect_tx(&b_full[s2], stage);
                         bulk_g2s(wst + (size_t)s2 * stage, src, stage, &b_full[s2]);
                     }
-                ww = W;      // nothing more to stream
-            }
-            while (xw < W || ww < W) {
-                bool progress = false;
-                if (xw < W) {
-                    const int buf = p.abufs == 2 ? (xtile & 1) : 0;
-                    if (mbar_test(&a_empty[buf], buf ? ae_par1 : ae_par0)) {
-                        if (buf) ae_par1 ^= 1; else ae_par0 ^= 1;
-                        const RbTile it = rb_tile(p, xw);
-                        const long long r0 = it.prow_u + it.t0 - p.pad2 - p.pad1;      // >= prow_u - TC_GAP >= 0
-                        mbar_expect_tx(&a_full[buf], 2 * a_tile);
-                        if (p.bulk_in) {
-                            planes_tile_g2s(abuf + (size_t)(buf * 2 + 0) * a_tile, p.inp, 0, 2 * (C / 8), r0, p.xr1, &a_full[buf]);
-                            planes_tile_g2s(abuf + (size_t)(buf * 2 + 1) * a_tile, p.inp, 0, 2 * (C / 8), r0 + 128, p.xr1, &a_full[buf]);
-                        } else {
-                            tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
-                            tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
+            } else {
+                int ws_ = 0; uint32_t wph = 1;
+#pragma unroll 1
+                for (int ww = blockIdx.x; ww < W; ww += wstep)
+#pragma unroll 1
+                    for (int wc = 0; wc < 2; ++wc) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(wc ? p.w2 : p.w1);
+                        const int kk = wc ? p.k2 : p.k1;
+#pragma unroll 1
+                        for (int wtap = 0; wtap < kk; ++wtap) {
+                            mbar_wait(&b_empty[ws_], wph);
+                            mbar_expect_tx(&b_full[ws_], stage);
+                            bulk_g2s(wst + (size_t)ws_ * stage, src + (size_t)wtap * stage, stage, &b_full[ws_]);
+                            if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
                         }
-                        xw += wstep; ++xtile;
-                        progress = true;
                     }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= x-tile producer (warp 21): one thread, blocking =====================================================
+        if (lane == 0) {
+            uint32_t ae_par0 = 1, ae_par1 = 1;
+            int xtile = 0;
+#pragma unroll 1
+            for (int xw = blockIdx.x; xw < W; xw += wstep, ++xtile) {
+                const int buf = p.abufs == 2 ? (xtile & 1) : 0;
+                if (buf) { mbar_wait(&a_empty[1], ae_par1); ae_par1 ^= 1; } else { mbar_wait(&a_empty[0], ae_par0); ae_par0 ^= 1; }
+                const RbTile it = rb_tile(p, xw);
+                const long long r0 = it.prow_u + it.t0 - p.pad2 - p.pad1;      // >= prow_u - TC_GAP >= 0
+                mbar_expect_tx(&a_full[buf], 2 * a_tile);
+                if (p.bulk_in) {
+                    planes_tile_g2s(abuf + (size_t)(buf * 2 + 0) * a_tile, p.inp, 0, 2 * (C / 8), r0, p.xr1, &a_full[buf]);
+                    planes_tile_g2s(abuf + (size_t)(buf * 2 + 1) * a_tile, p.inp, 0, 2 * (C / 8), r0 + 128, p.xr1, &a_full[buf]);
+                } else {
+                    tma_load_3d(abuf + (size_t)(buf * 2 + 0) * a_tile, &imap, 0, (int)r0, 0, &a_full[buf]);
+                    tma_load_3d(abuf + (size_t)(buf * 2 + 1) * a_tile, &imap, 0, (int)r0 + 128, 0, &a_full[buf]);
                 }
-                if (ww < W) {
-                    if (mbar_test(&b_empty[ws_], wph)) {
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(wc ? p.w2 : p.w1) + (size_t)wtap * stage;
-                        mbar_expect_tx(&b_full[ws_], stage);
-                        bulk_g2s(wst + (size_t)ws_ * stage, src, stage, &b_full[ws_]);
-                        if (++ws_ == p.nb) { ws_ = 0; wph ^= 1; }
-                        if (++wtap == (wc ? p.k2 : p.k1)) { wtap = 0; if (++wc == 2) { wc = 0; ww += wstep; } }
-                        progress = true;
-                    }
-                }
-                if (!progress) __nanosleep(32);
             }
         }
         __syncwarp();

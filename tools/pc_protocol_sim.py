@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Discrete-event model of pc_fused.cuh's mbarrier protocol (issuers x4, epilogue warps x16, producer), CPU only.
+"""Discrete-event model of pc_fused.cuh's mbarrier protocol (issuers x4, epilogue warps x16, weight producer, tile producer), CPU only.
 
 mbarrier parity waits cannot tell phase n from phase n + 2; a role that skips a phase of a barrier deadlocks or — worse — passes
 early.  Every wait here carries the phase it MEANS; the model asserts that the wait passes on exactly that phase, and that every
@@ -93,6 +93,7 @@ def simulate(seed, nst, nb, npairs, nchunks, nitems, mode, rs, SPU=2, acc_first=
     def issuer(slot, b):
         af_k = 0; e_k = -1; ring0 = 0; prev_tg = -1; mma_done = [0.0]
         fills = {}                                           # ring slot -> fills seen
+        rs0, rp0 = [slot], [0]                               # the kernel's incremental ring position
 
         def commit(bar):                                     # tcgen05.commit: arrives when this thread's prior MMAs are done
             sim.at(max(0.0, mma_done[0] - sim.t) + R.uniform(20, 200), lambda: bar.arrive(sim))
@@ -112,6 +113,10 @@ def simulate(seed, nst, nb, npairs, nchunks, nitems, mode, rs, SPU=2, acc_first=
                 r = q % nb
                 k = fills.get(r, 0); fills[r] = k + 1
                 assert (q // nb) == k, "ring walk mismatch"
+                assert r == rs0[0] and (k & 1) == rp0[0], "incremental ring walk mismatch"
+                rs0[0] += 2
+                if rs0[0] >= nb:
+                    rs0[0] -= nb; rp0[0] ^= 1
                 yield ("wait", b_full[r], k & 1, k)
                 if own and active:
                     yield ("delay", R.uniform(100, 600))
@@ -145,64 +150,55 @@ def simulate(seed, nst, nb, npairs, nchunks, nitems, mode, rs, SPU=2, acc_first=
             else:
                 yield ("delay", R.uniform(200, 2500))
 
-    def producer():
-        xw = w0; ae_k = -1
-        rw = w0 if rs else w1; sf_k = [-1, -1]; rslot = 0
-        ww = w0; wstage = 0; wq2 = 0; ws = 0; fill = 0
-        while xw < w1 or ww < w1 or rw < w1:
-            progress = False
-            if xw < w1 and test(a_empty, ae_k & 1):
-                if ae_k >= 0 and a_empty.phase != ae_k + 1:
-                    sim.errors.append("producer passed a_empty at phase %d meant %d" % (a_empty.phase, ae_k))
-                ae_k += 1
-                a_full.arrive(sim, tx=1)
-                sim.at(R.uniform(500, 4000), lambda: a_full.complete_tx(sim, 1))
-                xw = min(w1, (xw // npairs + 1) * npairs)
-                progress = True
-            if rw < w1:
-                chunk = (rw % npairs) * 2 + rslot
-                act = chunk < nchunks
-                need = act and ((chunk % 2 == 0) or not acc_first)
-                adv = not act
-                if act and test(s_free[rslot], sf_k[rslot] & 1):
-                    if sf_k[rslot] >= 0 and s_free[rslot].phase != sf_k[rslot] + 1:
-                        sim.errors.append("producer passed s_free%d at phase %d meant %d" % (rslot, s_free[rslot].phase, sf_k[rslot]))
-                    sf_k[rslot] += 1
-                    adv = True; progress = True
-                if act and adv and not need:
-                    r_full[rslot].arrive(sim)
-                if act and adv and need:
-                    bar = r_full[rslot]
-                    bar.arrive(sim, tx=1)
-                    sim.at(R.uniform(300, 2500), (lambda bb: (lambda: bb.complete_tx(sim, 1)))(bar))
-                if adv:
-                    rslot += 1
-                    if rslot == 2:
-                        rslot = 0; rw += 1
-            if ww < w1:
-                k = fill // nb                                  # this is fill k of ring slot ws: needs release k - 1
-                if test(b_empty[ws], (k - 1) & 1):
-                    if k >= 1 and b_empty[ws].phase != k:
-                        sim.errors.append("producer passed b_empty%d at phase %d meant %d" % (ws, b_empty[ws].phase, k - 1))
+    def weight_producer():                      # warp 20: tight blocking loop over the ring
+        fill = 0
+        for w in range(w0, w1):
+            for st in range(nst):
+                for q in range(2):
+                    ws = fill % nb; k = fill // nb     # fill k of ring slot ws needs release k - 1
+                    if k >= 1:
+                        yield ("wait", b_empty[ws], (k - 1) & 1, k - 1)
                     bar = b_full[ws]
                     bar.arrive(sim, tx=1)
                     sim.at(R.uniform(300, 3000), (lambda bb: (lambda: bb.complete_tx(sim, 1)))(bar))
                     fill += 1
-                    ws = (ws + 1) % nb
-                    wq2 += 1
-                    if wq2 == 2:
-                        wq2 = 0; wstage += 1
-                        if wstage == nst:
-                            wstage = 0; ww += 1
-                    progress = True
-            yield ("poll",)
+                    yield ("delay", R.uniform(20, 120))
+
+    def tile_producer():                        # warp 21: activation tile + residual tiles, in item order, blocking
+        ae_k = -1; sf_k = [-1, -1]; prev_tg = -1
+        for w in range(w0, w1):
+            pair, tg = w % npairs, w // npairs
+            if tg != prev_tg:
+                if ae_k >= 0:
+                    yield ("wait", a_empty, ae_k & 1, ae_k)
+                ae_k += 1
+                a_full.arrive(sim, tx=1)
+                sim.at(R.uniform(500, 4000), lambda: a_full.complete_tx(sim, 1))
+            prev_tg = tg
+            if rs:
+                for rslot in range(2):
+                    chunk = pair * 2 + rslot
+                    if chunk >= nchunks:
+                        continue
+                    need = (chunk % 2 == 0) or not acc_first
+                    if sf_k[rslot] >= 0:
+                        yield ("wait", s_free[rslot], sf_k[rslot] & 1, sf_k[rslot])
+                    sf_k[rslot] += 1
+                    bar = r_full[rslot]
+                    if need:
+                        bar.arrive(sim, tx=1)
+                        sim.at(R.uniform(300, 2500), (lambda bb: (lambda: bb.complete_tx(sim, 1)))(bar))
+                    else:
+                        bar.arrive(sim)
+            yield ("delay", R.uniform(20, 200))
 
     for s in range(2):
         for b in range(2):
             sim.spawn("issuer(s%d,b%d)" % (s, b), issuer(s, b))
         for wi in range(8):
             sim.spawn("epi(s%d,w%d)" % (s, wi), epilogue(s, wi))
-    sim.spawn("producer", producer())
+    sim.spawn("weights", weight_producer())
+    sim.spawn("tiles", tile_producer())
     ok = sim.run()
     return ok, sim
 

@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+P="timeout -s KILL 75 python tools/pc_probe.py single_speaker_fast"
+STTS_PC_FUSED=0 $P gpurun_out/probe_ref.npy 2>&1 | tail -2
+[ -f gpurun_out/probe_ref.npy ] || { echo "reference probe failed"; exit 1; }
+export PROBE_REF=gpurun_out/probe_ref.npy
+STTS_PC_FUSED=1 $P 2>&1 | tail -2; rc2=${PIPESTATUS[0]}
+STTS_PC_FUSED=3 $P 2>&1 | tail -2; rc3=${PIPESTATUS[0]}
+PROBE_TENSOR=2 $P 2>&1 | tail -2; rc4=${PIPESTATUS[0]}
+echo "rc: $rc2 $rc3 $rc4"
+if [ "$rc2" != "0" ] || [ "$rc3" != "0" ]; then echo "probe failed: stop"; exit 1; fi
+for CFG in "default:" "pc3:STTS_PC_FUSED=3" "pc3dbg7:STTS_PC_FUSED=3 STTS_PC_DBG=7"; do
+  NAME=${CFG%%:*}; ENVS=${CFG#*:}
+  env $ENVS timeout -s KILL 150 python bench.py --no-cpu-baseline --steps 5 > gpurun_out/r2w_bench_$NAME.json 2>/dev/null
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/r2w_bench_$NAME.json")); print("$NAME", round(d["ms_per_step"],3), {k:round(v,3) for k,v in d["stage_ms_last_step"].items()}, {k:round(v["ms"],3) for k,v in d["conv_classes"].items()})
+except Exception as e: print("$NAME failed", e)
+PY
+done
+STTS_PC_FUSED=3 STTS_PC_TRACE=1 STTS_PC_TRACE_FILE=gpurun_out/pc_tl2 STTS_B200_LIB=tools/_build/libstts_b200_trace.so timeout -s KILL 120 python bench.py --steps 1 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep PCTRACE | head -3
+echo "== parity PC_FUSED=3"; STTS_PC_FUSED=3 timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -2
