@@ -179,6 +179,29 @@ int stts_test_rbpair(int device, int mode, const float* rec1, int64_t n1, const 
 int stts_debug_pack_weights(const float* w, int32_t k, int32_t inCh, int32_t outCh, int32_t usteps, int32_t* meta,
                             uint16_t** halves, int64_t* n_halves);
 
+/* ---- batched GRU grapheme-to-phoneme for out-of-vocabulary English words ----------------------
+ * Replaces the Eigen GRU the reference's English frontend runs one word at a time: gru_cell / gru
+ * (src/engipa/EnglishText2Id.cpp:270-313) and the encoder + greedy decoder of getIPAId (:496-545).  The frontend's
+ * dictionary lookup, the phone -> IPA string tables and the IPA -> id map stay on the host (INTEGRATION.md shows the
+ * binding inside getIPAId).
+ *
+ * stts_g2p_create: gru_section points at the 12 GRU records at the start of the English frontend tail, i.e.
+ * model_blob + stts_nn_end_offset(e) for an English `.bin` (the constructor EnglishText2Id(modelData, offset),
+ * EnglishText2Id.cpp:61-126); *consumed_floats (optional) = floats read, the `offset` the reference constructor returns. */
+typedef struct stts_g2p stts_g2p;
+int stts_g2p_create(const float* gru_section, int64_t n_floats, int device, stts_g2p** out, int64_t* consumed_floats);
+void stts_g2p_destroy(stts_g2p* g);
+/* which: 0 hidden size, 1 phone-table size, 2 letter-table size, 3 embedding size, 4 maximum phones per word (20, :527). */
+int32_t stts_g2p_dim(const stts_g2p* g, int32_t which);
+/* One launch for n_words lower-cased words: letters = the words' bytes concatenated, offsets[n_words + 1] their bounds
+ * (the reference maps each BYTE: 'a'..'z' -> 3..28, anything else -> <unk>, :496-511).  phones[n_words][20] receives the
+ * predicted phone-table ids (the `preds` of :542), n_phones[n_words] their count.  Optional outputs (NULL to skip):
+ * enc_hidden[n_words][hidden] = encoder state after </s> (:519), first_logits[n_words][phones] = logits of the first
+ * decoder step (:534).  Host buffers; returns after the results are in them. */
+int stts_g2p_predict(stts_g2p* g, int32_t n_words, const char* letters, const int32_t* offsets, int32_t* phones, int32_t* n_phones,
+                     float* enc_hidden, float* first_logits);
+int64_t stts_g2p_kernel_launches(const stts_g2p* g);
+
 /* Replaces: tts_free_data, src/utils/utils.cpp:34-37. */
 void stts_free(void* p);
 

@@ -201,3 +201,54 @@ def eltwise(which, x):
     y = _take(p, (x.size,))
     lib().sref_free(p)
     return y
+
+
+class RefG2p:
+    """The reference's unmodified EnglishText2Id object + its GRU internals (oracle/ref_g2p.cpp)."""
+
+    def __init__(self, section: np.ndarray):
+        L = lib()
+        if not hasattr(L, "_g2p_bound"):
+            L.sref_g2p_create.restype = C.c_void_p
+            L.sref_g2p_create.argtypes = [C.c_void_p, C.c_int64]
+            for name in ("sref_g2p_consumed", "sref_g2p_hidden", "sref_g2p_phones"):
+                getattr(L, name).restype = C.c_int32
+                getattr(L, name).argtypes = [C.c_void_p]
+            L.sref_g2p_destroy.argtypes = [C.c_void_p]
+            L.sref_g2p_ipa_ids.restype = C.c_int32
+            L.sref_g2p_ipa_ids.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32]
+            L.sref_g2p_word.restype = C.c_int32
+            L.sref_g2p_word.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L._g2p_bound = True
+        sec = _f32(section)
+        self._h = L.sref_g2p_create(sec.ctypes.data, sec.size)
+        self.consumed = L.sref_g2p_consumed(self._h)
+        self.hidden = L.sref_g2p_hidden(self._h)
+        self.phones = L.sref_g2p_phones(self._h)
+
+    def ipa_ids(self, text: str) -> list[int]:
+        """EnglishText2Id::getIPAId(text), unmodified (EnglishText2Id.cpp:456-609)."""
+        out = np.zeros(65536, np.int32)
+        n = lib().sref_g2p_ipa_ids(self._h, text.encode("utf-8"), out.ctypes.data, out.size)
+        return out[:n].tolist()
+
+    def word(self, word: bytes | str):
+        """The out-of-vocabulary branch (:496-545) over the reference's gru / gru_cell: (preds, hidden, logits0)."""
+        if isinstance(word, str):
+            word = word.encode("utf-8")
+        preds = np.zeros(20, np.int32)
+        hid = np.zeros(self.hidden, np.float32)
+        lg = np.zeros(self.phones, np.float32)
+        n = lib().sref_g2p_word(self._h, word, preds.ctypes.data, hid.ctypes.data, lg.ctypes.data)
+        return preds[:n].tolist(), hid, lg
+
+    def close(self):
+        if self._h:
+            lib().sref_g2p_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

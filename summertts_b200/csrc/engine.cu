@@ -2023,3 +2023,5 @@ int stts_last_timing(const stts_engine* e, float* ms, int32_t n) {
 }
 
 }  // extern "C"
+
+#include "g2p.cuh"   // batched GRU g2p for out-of-vocabulary English words: stts_g2p_*

@@ -27,7 +27,10 @@ ABI_SYMBOLS = [
     "stts_kernel_launches", "stts_stream", "stts_set_tensor_path", "stts_free", "stts_last_error",
     "stts_describe_model", "stts_version", "stts_profile_enable", "stts_profile_fetch",
     "stts_test_conv1d", "stts_debug_pack_weights", "stts_test_rbpair", "stts_tensor_fallbacks", "stts_infer_stream", "stts_create_cached",
+    "stts_g2p_create", "stts_g2p_destroy", "stts_g2p_dim", "stts_g2p_predict", "stts_g2p_kernel_launches",
 ]
+
+STTS_OK, STTS_E_ARG, STTS_E_FORMAT, STTS_E_UNSUPPORTED, STTS_E_CUDA, STTS_E_NOMEM = 0, -1, -2, -3, -4, -5   # include/stts_b200.h
 
 _lib = None
 
@@ -329,3 +332,56 @@ def debug_pack_weights(w, usteps=0):
 def ttsLoadModel(path: str) -> np.ndarray:
     """Mirror of ttsLoadModel (src/utils/utils.cpp:8-32): whole file as float32."""
     return np.fromfile(path, dtype=np.float32)
+
+
+class G2p:
+    """Batched GRU grapheme-to-phoneme on the GPU (stts_g2p_*): the out-of-vocabulary branch of the reference's
+    EnglishText2Id::getIPAId (src/engipa/EnglishText2Id.cpp:496-545) for many words in one launch.
+    `section` = the English model's floats from stts_nn_end_offset on (the reference constructor's `modelData + offset`)."""
+
+    def __init__(self, section: np.ndarray, device: int = 0):
+        self._L = L = load_library()
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        L.stts_g2p_create.argtypes = [vp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+        L.stts_g2p_destroy.argtypes = [vp]
+        L.stts_g2p_dim.argtypes = [vp, i32]
+        L.stts_g2p_dim.restype = i32
+        L.stts_g2p_predict.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+        L.stts_g2p_kernel_launches.argtypes = [vp]
+        L.stts_g2p_kernel_launches.restype = i64
+        sec = np.ascontiguousarray(section, dtype=np.float32)
+        h, used = vp(), i64()
+        _check(L.stts_g2p_create(sec.ctypes.data, sec.size, int(device), C.byref(h), C.byref(used)))
+        self._h = h
+        self.consumed = int(used.value)
+        self.hidden, self.phones, self.letters, self.emb, self.max_steps = (int(L.stts_g2p_dim(h, k)) for k in range(5))
+
+    def predict(self, words, debug: bool = False):
+        """words: lower-cased str / bytes.  Returns a list of phone-id lists (+ encoder states and first-step logits when debug)."""
+        ws = [w.encode("utf-8") if isinstance(w, str) else bytes(w) for w in words]
+        n = len(ws)
+        letters = np.frombuffer(b"".join(ws) or b"\0", dtype=np.uint8).copy()
+        offs = np.zeros(n + 1, np.int32)
+        offs[1:] = np.cumsum([len(w) for w in ws])
+        preds = np.zeros((max(n, 1), self.max_steps), np.int32)
+        cnt = np.zeros(max(n, 1), np.int32)
+        hid = np.zeros((max(n, 1), self.hidden), np.float32) if debug else None
+        lg = np.zeros((max(n, 1), self.phones), np.float32) if debug else None
+        _check(self._L.stts_g2p_predict(self._h, n, letters.ctypes.data, offs.ctypes.data, preds.ctypes.data, cnt.ctypes.data,
+                                        hid.ctypes.data if debug else None, lg.ctypes.data if debug else None))
+        out = [preds[i, :cnt[i]].tolist() for i in range(n)]
+        return (out, hid, lg) if debug else out
+
+    def kernel_launches(self) -> int:
+        return int(self._L.stts_g2p_kernel_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.stts_g2p_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
