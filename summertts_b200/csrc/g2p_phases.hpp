@@ -8,7 +8,7 @@
 //
 // Every function below is the work of ONE thread `tid` between two block barriers; all indexing of the kernel lives
 // here.  The file is plain C++ when STTS_HD is empty, so tests/g2p_host_harness.cpp runs the very same phases thread
-// by thread on the CPU against the oracle (the GPU box is not needed to check the indexing).
+// by thread on the CPU against the reference results (the GPU box is not needed to check the indexing).
 //
 // Memory layout (as stored in the `.bin`: Eigen column-major `Map<MatrixXf>(p, rows, cols)` -> element (r, c) at
 // p[r + c * rows], EnglishText2Id.cpp:75-123):
