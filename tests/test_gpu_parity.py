@@ -209,6 +209,35 @@ def test_speaker_id_clamp(native_lib):
     E.close()
 
 
+def test_config5_multi_speakers_batch64(native_lib):
+    """BASELINE config 5 as worded: multi_speakers.bin (stochastic duration predictor + spline flows + speaker conditioning +
+    HiFi-GAN down to 4 channels), 64 synthetic 128-id utterances in ONE batch, a different speaker per utterance, the model's
+    own durations.  Sampled utterances: bit-identical to their stand-alone run, and frame count exact / PCM within the `multi`
+    tolerance against the compiled reference run on the same ids and speaker."""
+    blob = find_model("multi_speakers")
+    if blob is None:
+        pytest.skip("shipped model did not travel")
+    rng = np.random.default_rng(55)
+    E = engine.SynthesizerTrn(blob)
+    nspk = E.getSpeakerNum()
+    utts = [synth_ids(rng, 128) for _ in range(64)]
+    sids = [(7 * i + 3) % nspk for i in range(64)]
+    out = E.infer_batch(utts, sids=sids)
+    assert len(out) == 64 and all(o.size > 0 and o.size % 256 == 0 for o in out)
+    for i in (0, 21, 63):
+        assert np.array_equal(E.infer_ids(utts[i], sid=sids[i]), out[i])
+    assert E.tensor_fallbacks() == 0
+    if ref.available():
+        ref.set_threads(8)
+        R = ref.RefModel(blob)
+        for i in (5, 40):
+            r = R.infer(utts[i], sid=sids[i], dumps=False)
+            assert r.S == out[i].size, (r.S, out[i].size)
+            _pcm_ok(out[i], r.pcm, 2, 1e-4)
+        R.close()
+    E.close()
+
+
 def test_native_kernels_ran(native_lib, fast_blob):
     E = engine.SynthesizerTrn(fast_blob)
     n0 = E.kernel_launches()
