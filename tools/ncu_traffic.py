@@ -11,7 +11,8 @@ import sys
 
 
 def rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i rep --page raw --csv` text saved on the GPU box (reports above the gpurun size cap stay there)
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(out.splitlines()))
     hdr, units = r[0], r[1]
     return hdr, units, r[2:]
