@@ -13,10 +13,14 @@
 // FMAs.  The input half of each cell is a table lookup (emb . W_ih^T + b_ih per token, built once at create time), so a
 // step is one GEMV, not two.  Bound: L2 -> SM bandwidth of the W_hh stream (786 KB per step per CTA).
 #pragma once
+#include <cooperative_groups.h>
 #define STTS_HD __host__ __device__
 #include "g2p_phases.hpp"
 
 namespace stts {
+
+// kernel a new handle uses unless STTS_G2P_KERNEL says otherwise: 0 = streaming (g2p_words_kernel), 1 = cluster-resident
+constexpr int G2P_DEFAULT_KERNEL = 0;
 
 struct G2pDev {
     int H = 0, E = 0, Vin = 0, Vout = 0;
@@ -111,6 +115,121 @@ __global__ void __launch_bounds__(1024) g2p_words_kernel(G2pDev m, G2pBatch b) {
     if (tid < G2P_WPC && wlen[tid] >= 0) b.npreds[widx[tid]] = npred[tid];
 }
 
+
+// Cluster-resident variant: see g2p_phases.hpp.  Launched with a cluster dimension of G2P_CL = 8; gridDim.x / 8 clusters walk
+// the word groups (G2P_WG = 8 words each, sorted by length) round-robin, so W_hh / fc_w are read from L2 once per launch.
+__global__ void __launch_bounds__(256, 1) g2p_cluster_kernel(G2pDev m, G2pBatch b, int ngroups) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / G2P_CL, ncl = gridDim.x / G2P_CL;
+    extern __shared__ __align__(16) float g2p_sm[];
+    const G2pClDims d = g2p_cl_dims(m.H, m.Vout);
+    const int H = d.H, HW = d.H * G2P_WG;
+    float* We = g2p_sm;                                  // [H][R]  encoder W_hh slice
+    float* Wd = We + H * d.R;                            // [H][R]  decoder W_hh slice
+    float* Fw = Wd + H * d.R;                            // [H][VS] fc_w slice
+    float* hb = Fw + H * d.VS;                           // [2][H][WG]
+    float* gs = hb + 2 * HW;                             // [R][WG]
+    float* lg = gs + d.R * G2P_WG;                       // [VS * CL][WG]
+    int* tok = (int*)(lg + d.VS * G2P_CL * G2P_WG);      // [WG] (every CTA keeps the same copy)
+    int* npred = tok + G2P_WG;
+    int* wlen = npred + G2P_WG;
+    int* woff = wlen + G2P_WG;
+    int* widx = woff + G2P_WG;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int off_h = (int)(hb - g2p_sm), off_lg = (int)(lg - g2p_sm);
+    float* peer[G2P_CL];                                 // every CTA's shared-memory block, as seen from here (DSMEM)
+#pragma unroll
+    for (int rk = 0; rk < G2P_CL; ++rk) peer[rk] = cluster.map_shared_rank(g2p_sm, rk);
+
+    for (int i = tid; i < H * d.R; i += nt) {
+        g2p_cl_load_w(i, d, rank, m.enc_whh, We);
+        g2p_cl_load_w(i, d, rank, m.dec_whh, Wd);
+    }
+    for (int i = tid; i < H * d.VS; i += nt) g2p_cl_load_fc(i, d, rank, m.fcw, Fw);
+    __syncthreads();
+
+    for (int g = cid; g < ngroups; g += ncl) {
+        for (int i = tid; i < HW; i += nt) hb[i] = 0.f;                 // h0 = 0 in buffer 0
+        if (tid < G2P_WG) {
+            const int s = g * G2P_WG + tid;
+            const bool has = s < b.n_words;
+            const int w = has ? b.order[s] : 0;
+            widx[tid] = w;
+            woff[tid] = has ? b.offsets[w] : 0;
+            wlen[tid] = has ? b.offsets[w + 1] - b.offsets[w] : -1;
+            npred[tid] = 0;
+        }
+        __syncthreads();
+        int maxlen = -1;
+#pragma unroll
+        for (int w = 0; w < G2P_WG; ++w) maxlen = max(maxlen, wlen[w]);
+        cluster.sync();            // no peer writes into this CTA's buffers before they are initialised
+        int cur = 0;
+
+        for (int t = 0; t <= maxlen; ++t) {                              // encoder
+            if (tid < G2P_WG) {
+                const int L = wlen[tid];
+                tok[tid] = (L < 0 || t > L) ? -1 : (t == L ? G2P_EOS_IN : g2p_letter_id(b.letters[woff[tid] + t]));
+            }
+            __syncthreads();
+            for (int o = tid; o < 2 * d.R; o += nt) g2p_cl_gates_phase(o, d, rank, We, m.enc_bhh, m.enc_tab, tok, hb + cur * HW, gs);
+            __syncthreads();
+            {
+                float* hn[G2P_CL];
+#pragma unroll
+                for (int rk = 0; rk < G2P_CL; ++rk) hn[rk] = peer[rk] + off_h + (cur ^ 1) * HW;
+                for (int i = tid; i < d.HS * G2P_WG; i += nt) g2p_cl_update_phase(i, d, rank, m.enc_tab, tok, gs, hb + cur * HW, hn);
+            }
+            cluster.sync();        // every slice of the new state has landed everywhere
+            cur ^= 1;
+        }
+        if (rank == 0 && b.enc_hidden)
+            for (int i = tid; i < HW; i += nt) {
+                const int j = i / G2P_WG, w = i - j * G2P_WG;
+                if (wlen[w] >= 0) b.enc_hidden[(int64_t)widx[w] * H + j] = hb[cur * HW + i];
+            }
+
+        if (tid < G2P_WG) tok[tid] = wlen[tid] < 0 ? -1 : G2P_BOS_OUT;   // greedy decoder
+        __syncthreads();
+        for (int step = 0; step < G2P_MAX_STEPS; ++step) {
+            bool any = false;
+#pragma unroll
+            for (int w = 0; w < G2P_WG; ++w) any |= tok[w] >= 0;       // identical in every CTA of the cluster: uniform exit
+            if (!any) break;
+            for (int o = tid; o < 2 * d.R; o += nt) g2p_cl_gates_phase(o, d, rank, Wd, m.dec_bhh, m.dec_tab, tok, hb + cur * HW, gs);
+            __syncthreads();
+            {
+                float* hn[G2P_CL];
+#pragma unroll
+                for (int rk = 0; rk < G2P_CL; ++rk) hn[rk] = peer[rk] + off_h + (cur ^ 1) * HW;
+                for (int i = tid; i < d.HS * G2P_WG; i += nt) g2p_cl_update_phase(i, d, rank, m.dec_tab, tok, gs, hb + cur * HW, hn);
+            }
+            cluster.sync();
+            cur ^= 1;
+            {
+                float* lgs[G2P_CL];
+#pragma unroll
+                for (int rk = 0; rk < G2P_CL; ++rk) lgs[rk] = peer[rk] + off_lg;
+                for (int i = tid; i < d.VS * G2P_WG; i += nt) g2p_cl_logits_phase(i, d, rank, Fw, m.fcb, tok, hb + cur * HW, lgs);
+            }
+            cluster.sync();        // all logits slices are in every CTA
+            if (rank == 0 && step == 0 && b.first_logits)
+                for (int i = tid; i < d.V * G2P_WG; i += nt) {
+                    const int c = i / G2P_WG, w = i - c * G2P_WG;
+                    if (wlen[w] >= 0) b.first_logits[(int64_t)widx[w] * d.V + c] = lg[i];
+                }
+            if (tid < G2P_WG && tok[tid] >= 0)
+                g2p_cl_pick_phase(tid, d.V, lg, tok, npred, rank == 0 ? b.preds + (int64_t)widx[tid] * G2P_MAX_STEPS : nullptr);
+            __syncthreads();
+        }
+        if (rank == 0 && tid < G2P_WG && wlen[tid] >= 0) b.npreds[widx[tid]] = npred[tid];
+        __syncthreads();
+    }
+    cluster.sync();                // no CTA leaves while a peer may still write into its shared memory
+}
+
 }  // namespace stts
 
 struct stts_g2p {
@@ -125,6 +244,9 @@ struct stts_g2p {
     int64_t launches = 0;
     size_t smem = 0;
     int threads = 0;
+    int kernel = 0;            // 0 = streaming kernel (W_hh from L2 every step), 1 = cluster-resident kernel
+    size_t cl_smem = 0;
+    int cl_clusters = 0;       // co-resident clusters of 8 CTAs the device admits (cudaOccupancyMaxActiveClusters)
 
     template <typename T>
     T* dalloc(size_t n) {
@@ -218,6 +340,33 @@ static void g2p_build(stts_g2p* g, const float* sec, int64_t n, int64_t* consume
     m.dec_tab = dtab;
     if (g->smem > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(g2p_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    // cluster-resident kernel: eligible when the slices of both W_hh, of fc_w and the state fit one CTA's shared memory
+    const char* env = getenv("STTS_G2P_KERNEL");
+    const int want = env ? atoi(env) : G2P_DEFAULT_KERNEL;
+    g->kernel = 0;
+    if (want == 1 && H % G2P_CL == 0 && H % 8 == 0) {
+        const G2pClDims d = g2p_cl_dims(H, fcw.r);
+        const size_t bytes = (size_t)g2p_cl_smem_floats(d) * 4 + 5 * G2P_WG * 4;
+        int maxOptin = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device));
+        if (bytes <= (size_t)maxOptin) {
+            CUDA_CHECK(cudaFuncSetAttribute(g2p_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(G2P_CL);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = bytes;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = G2P_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, g2p_cluster_kernel, &cfg) == cudaSuccess && ncl > 0) {
+                g->kernel = 1; g->cl_smem = bytes; g->cl_clusters = ncl;
+            } else {
+                cudaGetLastError();    // not placeable on this device: the streaming kernel stays
+            }
+        }
+    }
 }
 
 static void g2p_predict(stts_g2p* g, int32_t n_words, const char* letters, const int32_t* offsets, int32_t* phones, int32_t* n_phones,
@@ -257,8 +406,22 @@ static void g2p_predict(stts_g2p* g, int32_t n_words, const char* letters, const
     b.preds = g->d_preds; b.npreds = g->d_npreds;
     b.enc_hidden = enc_hidden ? g->d_hidden : nullptr;
     b.first_logits = first_logits ? g->d_logits : nullptr;
-    const int ctas = (n_words + G2P_WPC - 1) / G2P_WPC;
-    g2p_words_kernel<<<ctas, g->threads, g->smem, g->stream>>>(g->m, b);
+    if (g->kernel == 1) {
+        const int ngroups = (n_words + G2P_WG - 1) / G2P_WG;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(G2P_CL * std::min(ngroups, g->cl_clusters));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = g->cl_smem;
+        cfg.stream = g->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = G2P_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, g2p_cluster_kernel, g->m, b, ngroups));
+    } else {
+        const int ctas = (n_words + G2P_WPC - 1) / G2P_WPC;
+        g2p_words_kernel<<<ctas, g->threads, g->smem, g->stream>>>(g->m, b);
+    }
     CUDA_CHECK(cudaGetLastError());
     g->launches += 1;
     CUDA_CHECK(cudaMemcpyAsync(phones, g->d_preds, (size_t)n_words * G2P_MAX_STEPS * 4, cudaMemcpyDeviceToHost, g->stream));
@@ -301,6 +464,8 @@ int32_t stts_g2p_dim(const stts_g2p* g, int32_t which) {
         case 2: return g->m.Vin;
         case 3: return g->m.E;
         case 4: return stts::G2P_MAX_STEPS;
+        case 5: return g->kernel;
+        case 6: return g->cl_clusters;
         default: return -1;
     }
 }

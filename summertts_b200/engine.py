@@ -355,6 +355,7 @@ class G2p:
         self._h = h
         self.consumed = int(used.value)
         self.hidden, self.phones, self.letters, self.emb, self.max_steps = (int(L.stts_g2p_dim(h, k)) for k in range(5))
+        self.kernel, self.clusters = int(L.stts_g2p_dim(h, 5)), int(L.stts_g2p_dim(h, 6))   # 0 streaming / 1 cluster-resident; co-resident clusters
 
     def predict(self, words, debug: bool = False):
         """words: lower-cased str / bytes.  Returns a list of phone-id lists (+ encoder states and first-step logits when debug)."""

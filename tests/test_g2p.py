@@ -107,6 +107,7 @@ def host_harness(tmp_path_factory):
     assert r.returncode == 0, r.stderr[-2000:]
     L = C.CDLL(so)
     L.g2p_host_predict.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.g2p_host_predict_cluster.argtypes = L.g2p_host_predict.argtypes + [C.c_int32]
     return L
 
 
@@ -116,8 +117,11 @@ def _pack(words):
     return letters, offs
 
 
+@pytest.mark.parametrize("kernel", ["stream", "cluster1", "cluster3", "cluster18"])
 @pytest.mark.parametrize("case", ["synth64", "ragged7", "small_dims"])
-def test_kernel_phases_on_cpu(host_harness, case):
+def test_kernel_phases_on_cpu(host_harness, case, kernel):
+    """Both kernels (W_hh streamed per step / resident in an 8-CTA cluster with the state exchanged through the peers' shared memory),
+    the cluster one with 1, 3 and 18 co-resident clusters walking the word groups."""
     if case == "small_dims":      # another hidden / table size: 3H = 96 < 4 * V = 148 (the logits phase sets the thread count)
         sec = gn.synthetic_section(5, hidden=32, emb=24, n_letters=29, n_phones=37, scale=4.0)
         words = [b"abcd", b"zyx", b"q", b"hellothere", b"kernel"]
@@ -129,8 +133,11 @@ def test_kernel_phases_on_cpu(host_harness, case):
     letters, offs = _pack(words)
     preds, cnt = np.full((n, 20), -9, np.int32), np.full(n, -9, np.int32)
     hid, lg = np.zeros((n, H), np.float32), np.zeros((n, V), np.float32)
-    host_harness.g2p_host_predict(sec.ctypes.data, n, letters.ctypes.data, offs.ctypes.data, preds.ctypes.data, cnt.ctypes.data, hid.ctypes.data,
-                                  lg.ctypes.data)
+    args = (sec.ctypes.data, n, letters.ctypes.data, offs.ctypes.data, preds.ctypes.data, cnt.ctypes.data, hid.ctypes.data, lg.ctypes.data)
+    if kernel == "stream":
+        assert host_harness.g2p_host_predict(*args) == 0
+    else:
+        assert host_harness.g2p_host_predict_cluster(*args, int(kernel[7:])) == 0
     for i, w in enumerate(words):
         p, h, l0 = gn.predict_word(m, w)
         assert np.abs(hid[i] - h).max() < 2e-5 and np.abs(lg[i] - l0).max() < 1e-4, w
@@ -149,11 +156,28 @@ def test_g2p_fails_loudly_without_gpu(native_lib):
 
 
 # ------------------------------------------------------------------------------------------------ GPU parity (C ABI)
-def _check_gpu(sec, words, want=None, live=None):
+KERNELS = [0, 1]      # 0 = g2p_words_kernel (streaming), 1 = g2p_cluster_kernel (cluster-resident weights, DSMEM exchange)
+
+
+def _make(sec, kernel):
     from summertts_b200 import engine
 
+    old = os.environ.get("STTS_G2P_KERNEL")
+    os.environ["STTS_G2P_KERNEL"] = str(kernel)
+    try:
+        g = engine.G2p(sec, device=0)
+    finally:
+        if old is None:
+            del os.environ["STTS_G2P_KERNEL"]
+        else:
+            os.environ["STTS_G2P_KERNEL"] = old
+    assert g.kernel == kernel, "kernel %d not selected (clusters admitted: %d)" % (kernel, g.clusters)
+    return g
+
+
+def _check_gpu(sec, words, want=None, live=None, kernel=0):
     m = gn.parse_section(sec)
-    g = engine.G2p(sec, device=0)
+    g = _make(sec, kernel)
     assert g.consumed == m["consumed"] and g.hidden == m["enc_w_hh"].shape[1] and g.phones == m["fc_w"].shape[0]
     got, hid, lg = g.predict(words, debug=True)
     assert g.kernel_launches() == 3      # two table builds at create + ONE launch for the whole batch
@@ -169,23 +193,41 @@ def _check_gpu(sec, words, want=None, live=None):
 
 
 @pytest.mark.gpu
-def test_gpu_g2p_synthetic_vs_golden(native_lib):
-    _check_gpu(_synth_section(), _words("synth"), _preds("synth"))
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_gpu_g2p_synthetic_vs_golden(native_lib, kernel):
+    _check_gpu(_synth_section(), _words("synth"), _preds("synth"), kernel=kernel)
 
 
 @pytest.mark.gpu
-def test_gpu_g2p_ragged_batches(native_lib):
-    """Word counts that do not fill the last CTA, 1-letter and 300-letter words, bytes outside a..z, another GRU size."""
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_gpu_g2p_ragged_batches(native_lib, kernel):
+    """Word counts that do not fill the last CTA / word group, 1-letter and 300-letter words, bytes outside a..z, another GRU size,
+    and more word groups than co-resident clusters (every cluster walks several groups)."""
     sec = _synth_section()
     rng = np.random.default_rng(3)
     long_word = bytes(int(c) for c in rng.integers(97, 123, 300))
     for words in ([b"q"], [b"ab", b"it's", b"\xc3\xa9clair"], [long_word, b"a", b"bc", b"def", b"ghij"], _words("synth")[:13] + [long_word]):
-        _check_gpu(sec, words)
-    _check_gpu(gn.synthetic_section(5, hidden=32, emb=24, n_letters=29, n_phones=37, scale=4.0), [b"abcd", b"zyx", b"q", b"hellothere", b"kernel"])
+        _check_gpu(sec, words, kernel=kernel)
+    many = [bytes(int(c) for c in rng.integers(97, 123, int(rng.integers(2, 15)))) for _ in range(8 * 18 * 3 + 5)]
+    _check_gpu(sec, many, kernel=kernel)
+    _check_gpu(gn.synthetic_section(5, hidden=32, emb=24, n_letters=29, n_phones=37, scale=4.0), [b"abcd", b"zyx", b"q", b"hellothere", b"kernel"],
+               kernel=kernel)
 
 
 @pytest.mark.gpu
-def test_gpu_g2p_shipped_model(native_lib):
+def test_gpu_g2p_kernels_bit_identical(native_lib):
+    """Same accumulation order per output in both kernels: encoder states and logits are bit-identical, not just close."""
+    sec, words = _synth_section(), _words("synth")
+    a, b = _make(sec, 0), _make(sec, 1)
+    pa, ha, la = a.predict(words, debug=True)
+    pb, hb, lb = b.predict(words, debug=True)
+    assert pa == pb and np.array_equal(ha, hb) and np.array_equal(la, lb)
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_gpu_g2p_shipped_model(native_lib, kernel):
     """The shipped English model's GRU: phone ids == golden (compiled reference) and, through the frontend's tables, the IPA ids
     of the reference's unmodified getIPAId; against the live reference too where libstts_ref.so travelled."""
     sec = _real_section()
@@ -193,7 +235,7 @@ def test_gpu_g2p_shipped_model(native_lib):
         pytest.skip("shipped English model's GRU section did not travel")
     words = _words("real")
     live = ref.RefG2p(sec) if ref.available() else None
-    got = _check_gpu(sec, words, _preds("real"), live)
+    got = _check_gpu(sec, words, _preds("real"), live, kernel=kernel)
     want, off = G["real_ipa_ids"], G["real_ipa_offsets"]
     for i, p in enumerate(got):
         assert gn.preds_to_ipa_ids(p) == want[off[i]:off[i + 1]].tolist()

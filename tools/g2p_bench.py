@@ -26,14 +26,30 @@ def main():
         sec, weights = gn.synthetic_section(4242, scale=4.0), "synthetic seed 4242"
     rng = np.random.default_rng(0)
     words = [bytes(int(c) for c in rng.integers(97, 123, int(rng.integers(4, 13)))) for _ in range(n)]
-    g = engine.G2p(sec)
     out = {"weights": weights, "n_words": n, "letters_per_word": "4..12"}
-    for batch in (1, 64, 592, n):
-        g.predict(words[:batch])
-        best = 1e9
-        for _ in range(5):
-            t = time.perf_counter(); got = g.predict(words[:batch]); best = min(best, time.perf_counter() - t)
-        out["gpu_batch_%d" % batch] = {"ms": round(best * 1e3, 3), "words_per_s": round(batch / best)}
+    got = None
+    for kernel, name in ((0, "stream"), (1, "cluster")):     # STTS_G2P_KERNEL: W_hh streamed from L2 per step / resident in 8-CTA clusters
+        os.environ["STTS_G2P_KERNEL"] = str(kernel)
+        try:
+            g = engine.G2p(sec)
+        except engine.SttsError as e:
+            out[name] = {"error": str(e)}
+            continue
+        if g.kernel != kernel:
+            out[name] = {"error": "not selected (clusters admitted: %d)" % g.clusters}
+            continue
+        res = {"clusters": g.clusters} if kernel else {}
+        for batch in (1, 64, 144, 592, n):
+            g.predict(words[:batch])
+            best = 1e9
+            for _ in range(5):
+                t = time.perf_counter(); r = g.predict(words[:batch]); best = min(best, time.perf_counter() - t)
+            res["batch_%d" % batch] = {"ms": round(best * 1e3, 3), "words_per_s": round(batch / best)}
+        if got is not None:
+            res["ids_equal_to_stream"] = bool(r == got)
+        got = got if got is not None else r
+        out[name] = res
+        g.close()
     if ref.available():
         ref.set_threads(1)
         R = ref.RefG2p(sec)
