@@ -28,6 +28,9 @@ for k in 0 1; do
   tail -2 gpurun_out/${T}_ncu_g2p_k$k.log
 done
 stamp ncu-g2p
+timeout 200 ncu --set full --clock-control none --import-source on -k "regex:relattn|ms_tail" -s 20 -c 2 -f -o gpurun_out/${T}_ncu_full_misc python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_misc.log 2>&1
+[ -f gpurun_out/${T}_ncu_full_misc.ncu-rep ] && python tools/ncu_summary.py gpurun_out/${T}_ncu_full_misc.ncu-rep gpurun_out/${T}_ncu_full_misc_summary.csv > gpurun_out/${T}_ncu_key_metrics_misc.txt 2>&1
+stamp ncu-misc
 for k in 0 1; do
   timeout 120 compute-sanitizer --tool racecheck python tools/g2p_probe.py $k 40 > gpurun_out/${T}_sanitizer_racecheck_g2p_k$k.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_racecheck_g2p_k$k.txt
   timeout 120 compute-sanitizer --tool memcheck python tools/g2p_probe.py $k 40 > gpurun_out/${T}_sanitizer_memcheck_g2p_k$k.txt 2>&1; tail -3 gpurun_out/${T}_sanitizer_memcheck_g2p_k$k.txt
