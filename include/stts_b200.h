@@ -192,8 +192,9 @@ typedef struct stts_g2p stts_g2p;
 int stts_g2p_create(const float* gru_section, int64_t n_floats, int device, stts_g2p** out, int64_t* consumed_floats);
 void stts_g2p_destroy(stts_g2p* g);
 /* which: 0 hidden size, 1 phone-table size, 2 letter-table size, 3 embedding size, 4 maximum phones per word (20, :527),
- * 5 kernel in use (0 = W_hh streamed from L2 every step, 1 = W_hh resident in the shared memory of 8-CTA clusters; chosen at
- * create time, environment STTS_G2P_KERNEL overrides the default), 6 co-resident clusters the device admits (kernel 1). */
+ * 5 kernel choice of the handle: 0 = W_hh streamed from L2 every step, 1 = W_hh resident in the shared memory of 8-CTA clusters,
+ * 2 = per call (clusters up to 2048 words, streaming above; the default where the device admits the clusters; environment
+ * STTS_G2P_KERNEL overrides), 6 co-resident clusters the device admits, 7 kernel of the last stts_g2p_predict (0 / 1). */
 int32_t stts_g2p_dim(const stts_g2p* g, int32_t which);
 /* One launch for n_words lower-cased words: letters = the words' bytes concatenated, offsets[n_words + 1] their bounds
  * (the reference maps each BYTE: 'a'..'z' -> 3..28, anything else -> <unk>, :496-511).  phones[n_words][20] receives the

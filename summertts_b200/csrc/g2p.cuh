@@ -19,8 +19,13 @@
 
 namespace stts {
 
-// kernel a new handle uses unless STTS_G2P_KERNEL says otherwise: 0 = streaming (g2p_words_kernel), 1 = cluster-resident
-constexpr int G2P_DEFAULT_KERNEL = 0;
+// Kernel choice of a handle (environment STTS_G2P_KERNEL overrides the default): 0 = streaming kernel only (g2p_words_kernel),
+// 1 = cluster-resident kernel only, 2 = per call: the cluster-resident kernel up to G2P_AUTO_MAX_WORDS words, the streaming kernel
+// above.  Measured on B200 with the shipped model (profiles/r2_final_g2p_bench.json): 1 / 64 / 144 / 592 words 0.19 / 0.27 / 0.39 /
+// 1.33 ms on the cluster kernel against 1.05 / 1.40 / 1.44 / 1.79 ms streaming; at 4096 words the streaming kernel's 296 co-resident
+// CTAs win (6.2 vs 6.9 ms: 15 clusters walk 512 word groups).
+constexpr int G2P_DEFAULT_KERNEL = 2;
+constexpr int G2P_AUTO_MAX_WORDS = 2048;
 
 struct G2pDev {
     int H = 0, E = 0, Vin = 0, Vout = 0;
@@ -244,7 +249,8 @@ struct stts_g2p {
     int64_t launches = 0;
     size_t smem = 0;
     int threads = 0;
-    int kernel = 0;            // 0 = streaming kernel (W_hh from L2 every step), 1 = cluster-resident kernel
+    int kernel = 0;            // 0 = streaming kernel (W_hh from L2 every step), 1 = cluster-resident kernel, 2 = chosen per call
+    int last_kernel = -1;      // kernel of the last predict (0 / 1)
     size_t cl_smem = 0;
     int cl_clusters = 0;       // co-resident clusters of 8 CTAs the device admits (cudaOccupancyMaxActiveClusters)
 
@@ -344,7 +350,7 @@ static void g2p_build(stts_g2p* g, const float* sec, int64_t n, int64_t* consume
     const char* env = getenv("STTS_G2P_KERNEL");
     const int want = env ? atoi(env) : G2P_DEFAULT_KERNEL;
     g->kernel = 0;
-    if (want == 1 && H % G2P_CL == 0 && H % 8 == 0) {
+    if ((want == 1 || want == 2) && H % G2P_CL == 0 && H % 8 == 0) {
         const G2pClDims d = g2p_cl_dims(H, fcw.r);
         const size_t bytes = (size_t)g2p_cl_smem_floats(d) * 4 + 5 * G2P_WG * 4;
         int maxOptin = 0;
@@ -361,7 +367,7 @@ static void g2p_build(stts_g2p* g, const float* sec, int64_t n, int64_t* consume
             cfg.attrs = at; cfg.numAttrs = 1;
             int ncl = 0;
             if (cudaOccupancyMaxActiveClusters(&ncl, g2p_cluster_kernel, &cfg) == cudaSuccess && ncl > 0) {
-                g->kernel = 1; g->cl_smem = bytes; g->cl_clusters = ncl;
+                g->kernel = want; g->cl_smem = bytes; g->cl_clusters = ncl;
             } else {
                 cudaGetLastError();    // not placeable on this device: the streaming kernel stays
             }
@@ -406,7 +412,9 @@ static void g2p_predict(stts_g2p* g, int32_t n_words, const char* letters, const
     b.preds = g->d_preds; b.npreds = g->d_npreds;
     b.enc_hidden = enc_hidden ? g->d_hidden : nullptr;
     b.first_logits = first_logits ? g->d_logits : nullptr;
-    if (g->kernel == 1) {
+    const bool use_cluster = g->kernel == 1 || (g->kernel == 2 && n_words <= G2P_AUTO_MAX_WORDS);
+    g->last_kernel = use_cluster ? 1 : 0;
+    if (use_cluster) {
         const int ngroups = (n_words + G2P_WG - 1) / G2P_WG;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(G2P_CL * std::min(ngroups, g->cl_clusters));
@@ -466,6 +474,7 @@ int32_t stts_g2p_dim(const stts_g2p* g, int32_t which) {
         case 4: return stts::G2P_MAX_STEPS;
         case 5: return g->kernel;
         case 6: return g->cl_clusters;
+        case 7: return g->last_kernel;
         default: return -1;
     }
 }

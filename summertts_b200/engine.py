@@ -355,7 +355,7 @@ class G2p:
         self._h = h
         self.consumed = int(used.value)
         self.hidden, self.phones, self.letters, self.emb, self.max_steps = (int(L.stts_g2p_dim(h, k)) for k in range(5))
-        self.kernel, self.clusters = int(L.stts_g2p_dim(h, 5)), int(L.stts_g2p_dim(h, 6))   # 0 streaming / 1 cluster-resident; co-resident clusters
+        self.kernel, self.clusters = int(L.stts_g2p_dim(h, 5)), int(L.stts_g2p_dim(h, 6))   # 0 streaming / 1 cluster-resident / 2 per call; co-resident clusters
 
     def predict(self, words, debug: bool = False):
         """words: lower-cased str / bytes.  Returns a list of phone-id lists (+ encoder states and first-step logits when debug)."""
@@ -375,6 +375,10 @@ class G2p:
 
     def kernel_launches(self) -> int:
         return int(self._L.stts_g2p_kernel_launches(self._h))
+
+    def last_kernel(self) -> int:
+        """Kernel of the last predict: 0 streaming, 1 cluster-resident."""
+        return int(self._L.stts_g2p_dim(self._h, 7))
 
     def close(self):
         if getattr(self, "_h", None):

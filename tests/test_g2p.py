@@ -156,7 +156,7 @@ def test_g2p_fails_loudly_without_gpu(native_lib):
 
 
 # ------------------------------------------------------------------------------------------------ GPU parity (C ABI)
-KERNELS = [0, 1]      # 0 = g2p_words_kernel (streaming), 1 = g2p_cluster_kernel (cluster-resident weights, DSMEM exchange)
+KERNELS = [0, 1, 2]   # 0 = g2p_words_kernel (streaming), 1 = g2p_cluster_kernel (cluster-resident weights, DSMEM exchange), 2 = per call (default)
 
 
 def _make(sec, kernel):
@@ -210,6 +210,19 @@ def test_gpu_g2p_ragged_batches(native_lib, kernel):
         _check_gpu(sec, words, kernel=kernel)
     many = [bytes(int(c) for c in rng.integers(97, 123, int(rng.integers(2, 15)))) for _ in range(8 * 18 * 3 + 5)]
     _check_gpu(sec, many, kernel=kernel)
+    if kernel == 2:       # the per-call choice: clusters up to 2048 words, the streaming kernel above; and it is the default
+        g = _make(sec, 2)
+        big = (many * 5)[:2100]
+        assert g.predict(many[:50]) == [gn.predict_word(gn.parse_section(sec), w)[0] for w in many[:50]] and g.last_kernel() == 1
+        got = g.predict(big)
+        assert g.last_kernel() == 0 and got[:len(many)] == g.predict(many) and g.last_kernel() == 1
+        g.close()
+        from summertts_b200 import engine
+
+        assert os.environ.get("STTS_G2P_KERNEL") is None
+        d = engine.G2p(sec)
+        assert d.kernel == 2
+        d.close()
     _check_gpu(gn.synthetic_section(5, hidden=32, emb=24, n_letters=29, n_phones=37, scale=4.0), [b"abcd", b"zyx", b"q", b"hellothere", b"kernel"],
                kernel=kernel)
 

@@ -28,7 +28,7 @@ def main():
     words = [bytes(int(c) for c in rng.integers(97, 123, int(rng.integers(4, 13)))) for _ in range(n)]
     out = {"weights": weights, "n_words": n, "letters_per_word": "4..12"}
     got = None
-    for kernel, name in ((0, "stream"), (1, "cluster")):     # STTS_G2P_KERNEL: W_hh streamed from L2 per step / resident in 8-CTA clusters
+    for kernel, name in ((0, "stream"), (1, "cluster"), (2, "auto")):     # STTS_G2P_KERNEL: W_hh streamed from L2 per step / resident in 8-CTA clusters
         os.environ["STTS_G2P_KERNEL"] = str(kernel)
         try:
             g = engine.G2p(sec)
@@ -39,7 +39,7 @@ def main():
             out[name] = {"error": "not selected (clusters admitted: %d)" % g.clusters}
             continue
         res = {"clusters": g.clusters} if kernel else {}
-        for batch in (1, 64, 144, 592, n):
+        for batch in (1, 64, 144, 592, 2048, n):
             g.predict(words[:batch])
             best = 1e9
             for _ in range(5):
