@@ -7,11 +7,16 @@
 // Included at the end of engine.cu (uses its CUDA_CHECK / guard / error types).  All per-thread work is in
 // g2p_phases.hpp, shared with the CPU harness of the tests; this file holds the step loop, the launch and the C ABI.
 //
-// Kernel shape: one CTA per G2P_WPC = 4 words (sorted by length so a CTA's words finish together), 3H threads
-// (768 for the shipped model).  Per step every thread streams its column of W_hh (H floats, coalesced across the CTA,
-// L2-resident: 786 KB per matrix) against the four hidden states held in shared memory — one weight load feeds four
-// FMAs.  The input half of each cell is a table lookup (emb . W_ih^T + b_ih per token, built once at create time), so a
-// step is one GEMV, not two.  Bound: L2 -> SM bandwidth of the W_hh stream (786 KB per step per CTA).
+// Two kernels, chosen per call (G2P_DEFAULT_KERNEL below); the input half of each cell is a table lookup in both
+// (emb . W_ih^T + b_ih per token, built once at create time), so a step is one GEMV, not two:
+//  * g2p_cluster_kernel — a thread-block cluster of 8 CTAs keeps its slices of both W_hh matrices and of fc_w in shared
+//    memory for the whole launch (229 KB per CTA); the CTAs exchange hidden-state and logits slices by writing them into
+//    every peer's shared memory (DSMEM) before a cluster barrier.  8 words per cluster; bound by the per-step latency
+//    (shared-memory GEMV slice + cluster.sync).  Small and medium batches.
+//  * g2p_words_kernel — one CTA per G2P_WPC = 4 words (sorted by length so a CTA's words finish together), 3H threads
+//    (768 for the shipped model); per step every thread streams its column of W_hh (H floats, coalesced across the CTA,
+//    L2-resident: 786 KB per matrix) against the four hidden states held in shared memory — one weight load feeds four
+//    FMAs.  Bound by the bytes in flight per SM on the L2 -> SM stream; 296 co-resident CTAs: large batches.
 #pragma once
 #include <cooperative_groups.h>
 #define STTS_HD __host__ __device__
