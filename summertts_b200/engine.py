@@ -131,6 +131,7 @@ class SynthesizerTrn:
         self._L = L
         self.lang_type = L.stts_header_field(h, 1)
         self.dec_type = L.stts_header_field(h, 3)
+        self.nn_end = int(L.stts_nn_end_offset(h))   # float offset of the frontend tail (SynthesizerTrn.cpp:167)
 
     # -- reference API ---------------------------------------------------------------------------
     def getSpeakerNum(self) -> int:
